@@ -1,0 +1,42 @@
+"""pointmvsnet_b200 -- sm_100a implementation of PointMVSNet's PointFlow hot path.
+
+Mirrors the reference's import surface (pointmvsnet/model.py:8-12):
+    pointmvsnet_b200.networks            EdgeConv, EdgeConvNoC
+    pointmvsnet_b200.functions.functions get_pixel_grids
+    pointmvsnet_b200.functions.gather_knn gather_knn  (dgcnn_ext shim)
+    pointmvsnet_b200.utils.feature_fetcher FeatureFetcher
+    pointmvsnet_b200.utils.torch_utils   get_knn_3d
+    pointmvsnet_b200.nn.mlp / nn.conv    SharedMLP, Conv1d
+plus the new ``PointFlow`` module that replaces the ``point_flow`` closure
+(pointmvsnet/model.py:150-295).  ``install_as_pointmvsnet()`` aliases these modules
+under the reference's own names so an unchanged ``pointmvsnet/model.py`` imports them.
+"""
+__version__ = "0.1.0"
+
+
+def install_as_pointmvsnet(reference_root=None):
+    """Make ``import pointmvsnet.<hot-path module>`` resolve to this package.
+
+    With ``reference_root`` (a checkout of callmeray/PointMVSNet) the rest of the
+    reference package (model.py, dataset, config ...) is imported from there and only
+    the hot-path modules are replaced; see INTEGRATION.md."""
+    import importlib
+    import sys
+    if reference_root is not None and reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    mapping = {
+        "pointmvsnet.functions.dgcnn_ext": "pointmvsnet_b200.functions.dgcnn_ext",
+        "pointmvsnet.functions.gather_knn": "pointmvsnet_b200.functions.gather_knn",
+        "pointmvsnet.utils.feature_fetcher": "pointmvsnet_b200.utils.feature_fetcher",
+        "pointmvsnet.utils.torch_utils": "pointmvsnet_b200.utils.torch_utils",
+    }
+    for ref_name, ours in mapping.items():
+        sys.modules[ref_name] = importlib.import_module(ours)
+    if reference_root is not None:
+        import pointmvsnet.functions as pf  # the reference package itself
+        pf.dgcnn_ext = sys.modules["pointmvsnet.functions.dgcnn_ext"]
+        import pointmvsnet.networks as ref_networks
+        from pointmvsnet_b200 import networks as ours_networks
+        ref_networks.EdgeConv = ours_networks.EdgeConv
+        ref_networks.EdgeConvNoC = ours_networks.EdgeConvNoC
+        ref_networks.gather_knn = sys.modules["pointmvsnet.functions.gather_knn"].gather_knn

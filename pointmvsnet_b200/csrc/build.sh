@@ -1,0 +1,10 @@
+#!/usr/bin/env bash
+# Builds libpmvs_b200.so (sm_100a only) next to the Python package.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="${HERE}/../libpmvs_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared
+       --expt-relaxed-constexpr -Xptxas -v)
+"${NVCC}" "${FLAGS[@]}" -o "${OUT}" "${HERE}"/api.cu "${HERE}"/knn3d.cu "${HERE}"/fetch.cu "${HERE}"/edgeconv.cu "$@"
+echo "built ${OUT}"

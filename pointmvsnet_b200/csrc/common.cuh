@@ -1,0 +1,146 @@
+// Shared helpers for libpmvs_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pmvs_b200.h"
+
+namespace pmvs {
+
+// thread-local error text + process-wide launch counter (api.cu)
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return PMVS_ERR_CUDA;
+  }
+  count_launch();
+  return PMVS_OK;
+}
+
+#define PMVS_REQUIRE(cond, ...)     \
+  do {                              \
+    if (!(cond)) {                  \
+      pmvs::set_error(__VA_ARGS__); \
+      return PMVS_ERR_ARG;          \
+    }                               \
+  } while (0)
+
+#define PMVS_TRY(expr)           \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != PMVS_OK) return _rc; \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// BatchNorm (train mode) per-channel parameters derived from fp64 sums.
+struct BnCoef {
+  float mean, invstd;
+};
+__device__ __forceinline__ BnCoef bn_coef(double s1, double s2, double count, float eps) {
+  double m = s1 / count;
+  double var = s2 / count - m * m;  // biased batch variance
+  if (var < 0.0) var = 0.0;
+  BnCoef c;
+  c.mean = (float)m;
+  c.invstd = (float)(1.0 / sqrt(var + (double)eps));
+  return c;
+}
+// ATen's elementwise form: ((x - mean) * invstd) * gamma + beta
+__device__ __forceinline__ float bn_apply(float x, float mean, float invstd, float g, float b) {
+  return __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x, mean), invstd), g), b);
+}
+
+// ---- internal launchers shared between translation units ---------------------------
+int launch_knn3d(const float* xyz, int64_t* idx64, int32_t* idx32, int clouds, int D, int H, int W,
+                 int ksize, int knn, cudaStream_t st);
+int launch_transpose(const float* in, float* out, int batch, int R, int C, cudaStream_t st);
+
+struct GemmArgs {
+  const float* x;
+  int ldx;
+  const float* w;  // [cout, cin]
+  float* y;
+  int ldy;
+  int groups, rows_per_group, cin, cout;
+  // optional input BatchNorm+ReLU (stats of the producing layer): in_stats [groups, 2*cin] fp64
+  const double* in_stats;
+  const float* in_gamma;
+  const float* in_beta;
+  double in_count;
+  float eps;
+  // optional per-(group, out-channel) sum / sum-of-squares of y: out_stats [groups, 2*cout] fp64
+  double* out_stats;
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t st);
+
+struct EdgeArgs {
+  const float* le;  // [R, 2*cout]  (local | edge)
+  const int32_t* idx;  // [R, K]
+  double* stats;    // [groups, 4*cout]: sum_c, sumsq_c, sum_n, sumsq_n
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int concat_central;
+  float* out;
+  int ldo;
+  int groups, rows_per_group, N, K, cout;
+};
+int launch_edge_stats(const EdgeArgs& a, cudaStream_t st);
+int launch_edge_apply(const EdgeArgs& a, cudaStream_t st);
+
+struct FusedFetchParams {
+  const float* pyr[3];  // channels-last [B,V,hl,wl,C]
+  int hl[3], wl[3];
+  const float* depth_prev;  // [B,1,hp,wp]
+  const float* cam_blocks;  // [B, cam_block_floats(V)]
+  float* feature;           // [S,B,N,136]
+  float* xyz;               // [S,B,3,N]
+  int B, V, h, w, hp, wp, ratio;
+};
+int launch_cam_setup(const float* cam_params, const float* interval, const float* mean, const float* stdv,
+                     float* blocks, int B, int V, float kscale, cudaStream_t st);
+int launch_fused_fetch(const FusedFetchParams& p, cudaStream_t st);
+size_t cam_block_bytes(int B, int V);
+
+struct HeadArgs {
+  const float* h2;        // [S*B*N, 16]
+  const double* stats;    // [S, 32] sums / sums of squares of h2
+  const float* gamma;
+  const float* beta;
+  const float* w3;        // [16]
+  const float* depth_prev;  // [B,1,hp,wp]
+  const float* interval;    // [B]
+  float* depth_out;         // [B,1,h,w]
+  float* prob_out;          // [B,5,h,w] or NULL
+  float eps;
+  int B, S, ratio, h, w, hp, wp;
+};
+int launch_flow_head(const HeadArgs& a, cudaStream_t st);
+
+struct RunUpdate {
+  const double* stats;  // per group: [sum(C), sumsq(C)] at stride `gstride` doubles
+  float* run_mean;
+  float* run_var;
+  int C, off_sum, off_sq, gstride;
+  double count;  // values summed per group
+  double ncorr;  // element count nn.BatchNorm sees (for the unbiased running_var)
+};
+struct RunUpdateBatch {
+  RunUpdate u[9];
+  int n, groups;
+  float momentum;
+};
+int launch_bn_running_update(const RunUpdateBatch& rb, cudaStream_t st);
+
+}  // namespace pmvs

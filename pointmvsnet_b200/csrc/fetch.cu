@@ -1,0 +1,444 @@
+// Homography warp + multi-view feature fetch.
+//
+//  (1) pmvs_feature_fetch*: the stand-alone FeatureFetcher operator
+//      (reference utils/feature_fetcher.py:13-60), generic C / NCHW.
+//  (2) fused_fetch_kernel: rows a2-a9 of the hot path (reference model.py:153-204) in one
+//      launch: nearest depth upsample, pixel grid, hypothesis un-projection, projection into
+//      every view, pyramid resize composed with the bilinear fetch, variance over views,
+//      xyz normalisation, and the 136-channel point feature written points-major in the
+//      sub-cloud order the EdgeConv kernels consume.  One warp owns one pixel: lanes span
+//      the 112 pyramid channels (16 lanes x float4 on conv3, 8 on conv2, 4 on conv1), so a
+//      tap is one fully used 256/128/64-byte segment of the channels-last pyramid.
+//      Camera matrices for the CTA's batch element are staged into shared memory with one
+//      cp.async.bulk (TMA bulk copy) completing on an mbarrier.
+#include "common.cuh"
+
+namespace pmvs {
+
+// ---------------------------------------------------------------------------------------
+// camera block, one per batch element (floats)
+// ---------------------------------------------------------------------------------------
+constexpr int CB_KINV = 0;    // inverse of the scaled reference intrinsics, 3x3 row-major
+constexpr int CB_R0INV = 9;   // inverse reference rotation
+constexpr int CB_T0 = 18;     // reference translation
+constexpr int CB_MEAN = 21;
+constexpr int CB_STD = 24;
+constexpr int CB_INTERVAL = 27;
+constexpr int CB_VIEW = 28;   // per view: R[9], t[3], K[9] (scaled), pad[3]
+constexpr int CB_VSTRIDE = 24;
+__host__ __device__ constexpr int cam_block_floats(int V) { return CB_VIEW + CB_VSTRIDE * V; }
+
+__device__ void inv3x3(const double* m, double* o) {
+  const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+  const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+  const double det = a * A + b * B + c * C;
+  const double r = 1.0 / det;
+  o[0] = A * r;
+  o[1] = -(b * i - c * h) * r;
+  o[2] = (b * f - c * e) * r;
+  o[3] = B * r;
+  o[4] = (a * i - c * g) * r;
+  o[5] = -(a * f - c * d) * r;
+  o[6] = C * r;
+  o[7] = -(a * h - b * g) * r;
+  o[8] = (a * e - b * d) * r;
+}
+
+// cam_params [B,V,2,4,4] (io.py:31-45) -> camera blocks.  Mirrors model.py:54-57 (R, t,
+// R_inv), :159-163 (K rows 0,1 scaled), :169 (inverse of the reference K).
+__global__ void cam_setup_kernel(const float* __restrict__ cam_params, const float* __restrict__ interval,
+                                 const float* __restrict__ mean, const float* __restrict__ stdv,
+                                 float* __restrict__ blocks, int B, int V, float kscale) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float* out = blocks + (size_t)b * cam_block_floats(V);
+  for (int v = 0; v < V; ++v) {
+    const float* ext = cam_params + ((size_t)(b * V + v) * 2 + 0) * 16;
+    const float* intr = cam_params + ((size_t)(b * V + v) * 2 + 1) * 16;
+    float* o = out + CB_VIEW + v * CB_VSTRIDE;
+    float K[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        o[r * 3 + c] = ext[r * 4 + c];
+        float k = intr[r * 4 + c];
+        if (r < 2) k = __fmul_rn(k, kscale);
+        K[r * 3 + c] = k;
+        o[12 + r * 3 + c] = k;
+      }
+    for (int r = 0; r < 3; ++r) o[9 + r] = ext[r * 4 + 3];
+    o[21] = o[22] = o[23] = 0.f;
+    if (v == 0) {
+      double m[9], inv[9];
+      for (int q = 0; q < 9; ++q) m[q] = (double)K[q];
+      inv3x3(m, inv);
+      for (int q = 0; q < 9; ++q) out[CB_KINV + q] = (float)inv[q];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) m[r * 3 + c] = (double)ext[r * 4 + c];
+      inv3x3(m, inv);
+      for (int q = 0; q < 9; ++q) out[CB_R0INV + q] = (float)inv[q];
+      for (int r = 0; r < 3; ++r) out[CB_T0 + r] = ext[r * 4 + 3];
+    }
+  }
+  for (int r = 0; r < 3; ++r) {
+    out[CB_MEAN + r] = mean[b * 3 + r];
+    out[CB_STD + r] = stdv[b * 3 + r];
+  }
+  out[CB_INTERVAL] = interval[b];
+}
+
+// ---------------------------------------------------------------------------------------
+// shared projection math (feature_fetcher.py:36-53 + grid_sample's un-normalisation)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot3(const float* r, float x, float y, float z) {
+  return fmaf(r[2], z, fmaf(r[1], y, __fmul_rn(r[0], x)));
+}
+
+// pixel coordinate in the sampled map (align_corners=True round trip, feature_fetcher.py:51-53
+// then ATen grid_sampler_unnormalize): ((g + 1) / 2) * (size - 1), g = (u - .5)/(size-1)*2 - 1
+__device__ __forceinline__ float grid_coord(float u, int size) {
+  const float sm1 = (float)(size - 1);
+  const float g = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(u, 0.5f), sm1), 2.f), 1.f);
+  return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), sm1);
+}
+
+__device__ __forceinline__ void project(const float* R, const float* t, const float* K, float wx, float wy, float wz,
+                                        float& u, float& v) {
+  float xc = wx, yc = wy, zc = wz;
+  if (R != nullptr) {
+    xc = __fadd_rn(dot3(R + 0, wx, wy, wz), t[0]);
+    yc = __fadd_rn(dot3(R + 3, wx, wy, wz), t[1]);
+    zc = __fadd_rn(dot3(R + 6, wx, wy, wz), t[2]);
+  }
+  const float nx = __fdiv_rn(xc, zc), ny = __fdiv_rn(yc, zc);
+  u = dot3(K + 0, nx, ny, 1.f);
+  v = dot3(K + 3, nx, ny, 1.f);
+}
+
+__device__ __forceinline__ bool usable(float c) { return fabsf(c) < 1.0e8f; }  // false for NaN/inf
+
+// ---------------------------------------------------------------------------------------
+// (1) stand-alone FeatureFetcher
+// ---------------------------------------------------------------------------------------
+struct Taps {
+  int x0, y0;
+  float nw, ne, sw, se;
+  bool ok_w, ok_e, ok_n, ok_s;
+};
+__device__ __forceinline__ Taps make_taps(float ix, float iy, int W, int H) {
+  Taps t;
+  const float fx = floorf(ix), fy = floorf(iy);
+  t.x0 = (int)fx;
+  t.y0 = (int)fy;
+  const float ex = fx + 1.f, ey = fy + 1.f;
+  t.nw = __fmul_rn(__fsub_rn(ex, ix), __fsub_rn(ey, iy));
+  t.ne = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(ey, iy));
+  t.sw = __fmul_rn(__fsub_rn(ex, ix), __fsub_rn(iy, fy));
+  t.se = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(iy, fy));
+  t.ok_w = t.x0 >= 0 && t.x0 < W;
+  t.ok_e = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+  t.ok_n = t.y0 >= 0 && t.y0 < H;
+  t.ok_s = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+  return t;
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256)
+    feature_fetch_kernel(const float* __restrict__ maps, const float* __restrict__ pts, const float* __restrict__ Kmat,
+                         const float* __restrict__ Emat, float* __restrict__ out, float* __restrict__ grad_maps,
+                         int V, int C, int H, int W, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bv = blockIdx.y;
+  if (n >= N) return;
+  const int b = bv / V;
+  const float wx = pts[((size_t)b * 3 + 0) * N + n];
+  const float wy = pts[((size_t)b * 3 + 1) * N + n];
+  const float wz = pts[((size_t)b * 3 + 2) * N + n];
+  float R[9], t[3], K[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) K[q] = Kmat[(size_t)bv * 9 + q];
+  if (Emat != nullptr) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) R[r * 3 + c] = Emat[(size_t)bv * 12 + r * 4 + c];
+      t[r] = Emat[(size_t)bv * 12 + r * 4 + 3];
+    }
+  }
+  float u, v;
+  project(Emat ? R : nullptr, t, K, wx, wy, wz, u, v);
+  const float ix = grid_coord(u, W), iy = grid_coord(v, H);
+  const bool ok = usable(ix) && usable(iy);
+  Taps tp = make_taps(ok ? ix : -10.f, ok ? iy : -10.f, W, H);
+  const size_t plane = (size_t)H * W;
+  const size_t o_nw = (size_t)tp.y0 * W + tp.x0;
+  for (int c = 0; c < C; ++c) {
+    const size_t cb = ((size_t)bv * C + c) * plane;
+    if (!BACKWARD) {
+      const float* m = maps + cb;
+      float acc = 0.f;
+      if (tp.ok_n && tp.ok_w) acc = __fmul_rn(__ldg(m + o_nw), tp.nw);
+      if (tp.ok_n && tp.ok_e) acc = fmaf(__ldg(m + o_nw + 1), tp.ne, acc);
+      if (tp.ok_s && tp.ok_w) acc = fmaf(__ldg(m + o_nw + W), tp.sw, acc);
+      if (tp.ok_s && tp.ok_e) acc = fmaf(__ldg(m + o_nw + W + 1), tp.se, acc);
+      out[((size_t)bv * C + c) * N + n] = acc;
+    } else {
+      const float g = out[((size_t)bv * C + c) * N + n];  // `out` carries grad_out here
+      float* m = grad_maps + cb;
+      if (tp.ok_n && tp.ok_w) atomicAdd(m + o_nw, g * tp.nw);
+      if (tp.ok_n && tp.ok_e) atomicAdd(m + o_nw + 1, g * tp.ne);
+      if (tp.ok_s && tp.ok_w) atomicAdd(m + o_nw + W, g * tp.sw);
+      if (tp.ok_s && tp.ok_e) atomicAdd(m + o_nw + W + 1, g * tp.se);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// (2) fused warp + fetch + variance
+// ---------------------------------------------------------------------------------------
+
+// One axis of "bilinear sample of the bilinearly resized map" as <= 4 (index, weight)
+// pairs into the NATIVE map.  The resized map (F.interpolate, align_corners=False,
+// model.py:184) is never materialised: tap r of the sampled map is
+//   l0 * native[p0] + l1 * native[p1]   (ATen upsample_bilinear2d source index rule)
+// and the two sample taps (floor, floor+1) carry the grid_sample weights
+// (ATen grid_sampler_2d, zeros padding: out-of-range taps contribute nothing).
+struct Axis {
+  int i[4];
+  float w[4];
+};
+__device__ __forceinline__ void axis_entries(float coord, int out_size, int in_size, float scale, Axis& a) {
+  const float f = floorf(coord);
+  const int r0 = (int)f;
+  const float wt[2] = {__fsub_rn(f + 1.f, coord), __fsub_rn(coord, f)};
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int r = r0 + s;
+    const bool inb = r >= 0 && r < out_size;
+    float src = __fsub_rn(__fmul_rn(scale, (float)r + 0.5f), 0.5f);
+    if (src < 0.f) src = 0.f;
+    int p0 = (int)src;
+    if (p0 > in_size - 1) p0 = in_size - 1;
+    const int p1 = p0 + (p0 < in_size - 1 ? 1 : 0);
+    const float l1 = __fsub_rn(src, (float)p0);
+    const float l0 = __fsub_rn(1.f, l1);
+    a.i[2 * s] = p0;
+    a.i[2 * s + 1] = p1;
+    a.w[2 * s] = inb ? __fmul_rn(wt[s], l0) : 0.f;
+    a.w[2 * s + 1] = inb ? __fmul_rn(wt[s], l1) : 0.f;
+  }
+  // fold duplicate native indices so every native texel is loaded once
+  if (a.i[1] == a.i[0]) { a.w[0] += a.w[1]; a.w[1] = 0.f; }
+  if (a.i[3] == a.i[2]) { a.w[2] += a.w[3]; a.w[3] = 0.f; }
+  if (a.i[2] == a.i[0]) { a.w[0] += a.w[2]; a.w[2] = 0.f; }
+  else if (a.i[2] == a.i[1]) { a.w[1] += a.w[2]; a.w[2] = 0.f; }
+  if (a.i[3] == a.i[1]) { a.w[1] += a.w[3]; a.w[3] = 0.f; }
+  else if (a.i[3] == a.i[0]) { a.w[0] += a.w[3]; a.w[3] = 0.f; }
+}
+
+constexpr int FETCH_WARPS = 8;
+
+__global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const FusedFetchParams p) {
+  __shared__ __align__(16) float cam[cam_block_floats(PMVS_MAX_VIEWS)];
+  __shared__ __align__(8) unsigned long long bar;
+
+  const int b = blockIdx.y;
+  const int V = p.V;
+  // --- stage this batch element's camera block: one TMA bulk copy + mbarrier ------------
+  const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&bar);
+  const unsigned cam_addr = (unsigned)__cvta_generic_to_shared(cam);
+  const unsigned bytes = (unsigned)(cam_block_floats(V) * sizeof(float));
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float* src = p.cam_blocks + (size_t)b * cam_block_floats(V);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cam_addr),
+        "l"(src), "r"(bytes), "r"(bar_addr)
+        : "memory");
+  }
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar_addr)
+          : "memory");
+    }
+  }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pix = blockIdx.x * FETCH_WARPS + warp;
+  const int h = p.h, w = p.w;
+  if (pix >= h * w) return;
+  const int Y = pix / w, X = pix - Y * w;
+
+  // lane role: which pyramid level / channel quad this lane owns
+  int lvl, cq;  // level, float4 index inside the level
+  if (lane < 16) { lvl = 2; cq = lane; }
+  else if (lane < 24) { lvl = 1; cq = lane - 16; }
+  else if (lane < 28) { lvl = 0; cq = lane - 24; }
+  else { lvl = -1; cq = lane - 28; }
+  const int C = lvl == 2 ? 64 : (lvl == 1 ? 32 : 16);
+  const int ch_off = lvl == 2 ? 48 : (lvl == 1 ? 16 : 0);
+  const int hl = lvl >= 0 ? p.hl[lvl] : 1, wl = lvl >= 0 ? p.wl[lvl] : 1;
+  const float sx = (float)wl / (float)w, sy = (float)hl / (float)h;  // ATen area_pixel_compute_scale
+  const float* lbase = lvl >= 0 ? p.pyr[lvl] + cq * 4 : nullptr;
+
+  // nearest upsample of the previous depth (model.py:153-158; ATen nearest index rule)
+  const float nsy = (float)p.hp / (float)h, nsx = (float)p.wp / (float)w;
+  int ys = (int)floorf((float)Y * nsy), xs = (int)floorf((float)X * nsx);
+  ys = ys < p.hp - 1 ? ys : p.hp - 1;
+  xs = xs < p.wp - 1 ? xs : p.wp - 1;
+  const float dprev = __ldg(p.depth_prev + ((size_t)b * p.hp + ys) * p.wp + xs);
+
+  // uv = K_ref^-1 * (x + .5, y + .5, 1)   (functions.py:128-138, model.py:165-170)
+  const float px = (float)X + 0.5f, py = (float)Y + 0.5f;
+  const float uvx = dot3(cam + CB_KINV + 0, px, py, 1.f);
+  const float uvy = dot3(cam + CB_KINV + 3, px, py, 1.f);
+  const float uvz = dot3(cam + CB_KINV + 6, px, py, 1.f);
+  const float interval = cam[CB_INTERVAL];
+
+  // sub-cloud addressing (model.py:236-255): pixel (y*r+i, x*r+j) -> sub-cloud s=i*r+j
+  const int r = p.ratio;
+  const int hs = h / r, wsub = w / r;
+  const int yy = Y / r, ii = Y - yy * r, xx = X / r, jj = X - xx * r;
+  const int cloud = (ii * r + jj) * p.B + b;
+  const int Npts = PMVS_NUM_HYP * hs * wsub;
+  const float invV = (float)V;
+
+#pragma unroll 1
+  for (int m = 0; m < PMVS_NUM_HYP; ++m) {
+    const float dm = __fadd_rn(dprev, __fmul_rn(interval, (float)(m - 2)));  // model.py:174
+    const float cx = __fsub_rn(__fmul_rn(uvx, dm), cam[CB_T0 + 0]);
+    const float cy = __fsub_rn(__fmul_rn(uvy, dm), cam[CB_T0 + 1]);
+    const float cz = __fsub_rn(__fmul_rn(uvz, dm), cam[CB_T0 + 2]);
+    const float wx = dot3(cam + CB_R0INV + 0, cx, cy, cz);  // model.py:177
+    const float wy = dot3(cam + CB_R0INV + 3, cx, cy, cz);
+    const float wz = dot3(cam + CB_R0INV + 6, cx, cy, cz);
+
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll 1
+    for (int v = 0; v < V; ++v) {
+      const float* cv = cam + CB_VIEW + v * CB_VSTRIDE;
+      float u, vv;
+      project(cv, cv + 9, cv + 12, wx, wy, wz, u, vv);
+      const float ix = grid_coord(u, w), iy = grid_coord(vv, h);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lvl >= 0 && usable(ix) && usable(iy)) {
+        Axis ax, ay;
+        axis_entries(ix, w, wl, sx, ax);
+        axis_entries(iy, h, hl, sy, ay);
+        const float* vb = lbase + (size_t)(b * V + v) * hl * wl * C;
+#pragma unroll
+        for (int ey = 0; ey < 4; ++ey) {
+          if (ay.w[ey] != 0.f) {
+            const float* row = vb + (size_t)ay.i[ey] * wl * C;
+#pragma unroll
+            for (int ex = 0; ex < 4; ++ex) {
+              if (ax.w[ex] != 0.f) {
+                const float wgt = __fmul_rn(ay.w[ey], ax.w[ex]);
+                const float4 t = ldg4(row + (size_t)ax.i[ex] * C);
+                acc.x = fmaf(wgt, t.x, acc.x);
+                acc.y = fmaf(wgt, t.y, acc.y);
+                acc.z = fmaf(wgt, t.z, acc.z);
+                acc.w = fmaf(wgt, t.w, acc.w);
+              }
+            }
+          }
+        }
+      }
+      // model.py:188-189: mean over views of x and of x**2 (sum in view order)
+      s1.x = __fadd_rn(s1.x, acc.x); s1.y = __fadd_rn(s1.y, acc.y);
+      s1.z = __fadd_rn(s1.z, acc.z); s1.w = __fadd_rn(s1.w, acc.w);
+      s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
+      s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
+    }
+
+    const int n = (m * hs + yy) * wsub + xx;
+    float* frow = p.feature + ((size_t)cloud * Npts + n) * PMVS_FEAT_CH;
+    if (lvl >= 0) {
+      float4 o;  // model.py:190: E[x^2] - E[x]^2, unfused
+      float a;
+      a = __fdiv_rn(s1.x, invV); o.x = __fsub_rn(__fdiv_rn(s2.x, invV), __fmul_rn(a, a));
+      a = __fdiv_rn(s1.y, invV); o.y = __fsub_rn(__fdiv_rn(s2.y, invV), __fmul_rn(a, a));
+      a = __fdiv_rn(s1.z, invV); o.z = __fsub_rn(__fdiv_rn(s2.z, invV), __fmul_rn(a, a));
+      a = __fdiv_rn(s1.w, invV); o.w = __fsub_rn(__fdiv_rn(s2.w, invV), __fmul_rn(a, a));
+      st4(frow + ch_off + cq * 4, o);
+    }
+    // normalised xyz (model.py:46-48,193): tiled 8x into channels 112..135 and kept planar
+    const float nx = __fdiv_rn(__fsub_rn(wx, cam[CB_MEAN + 0]), cam[CB_STD + 0]);
+    const float ny = __fdiv_rn(__fsub_rn(wy, cam[CB_MEAN + 1]), cam[CB_STD + 1]);
+    const float nz = __fdiv_rn(__fsub_rn(wz, cam[CB_MEAN + 2]), cam[CB_STD + 2]);
+    int quad = -1;
+    if (lvl < 0) quad = cq;            // lanes 28..31 -> float4 0..3
+    else if (lane < 2) quad = 4 + lane;  // lanes 0,1   -> float4 4,5
+    if (quad >= 0) {
+      const int ph = quad % 3;  // float4 #q starts at component (4q) % 3 = q % 3
+      float4 o;
+      o.x = ph == 0 ? nx : (ph == 1 ? ny : nz);
+      o.y = ph == 0 ? ny : (ph == 1 ? nz : nx);
+      o.z = ph == 0 ? nz : (ph == 1 ? nx : ny);
+      o.w = o.x;
+      st4(frow + 112 + quad * 4, o);
+    }
+    if (lvl < 0 && cq < 3) {
+      p.xyz[((size_t)cloud * 3 + cq) * Npts + n] = cq == 0 ? nx : (cq == 1 ? ny : nz);
+    }
+  }
+}
+
+int launch_cam_setup(const float* cam_params, const float* interval, const float* mean, const float* stdv,
+                     float* blocks, int B, int V, float kscale, cudaStream_t st) {
+  cam_setup_kernel<<<cdiv(B, 32), 32, 0, st>>>(cam_params, interval, mean, stdv, blocks, B, V, kscale);
+  return check_launch("cam_setup_kernel");
+}
+
+int launch_fused_fetch(const FusedFetchParams& p, cudaStream_t st) {
+  dim3 grid(cdiv((long long)p.h * p.w, FETCH_WARPS), p.B);
+  fused_fetch_kernel<<<grid, FETCH_WARPS * 32, 0, st>>>(p);
+  return check_launch("fused_fetch_kernel");
+}
+
+size_t cam_block_bytes(int B, int V) { return (size_t)B * cam_block_floats(V) * sizeof(float); }
+
+}  // namespace pmvs
+
+extern "C" int pmvs_feature_fetch(const float* feature_maps, const float* pts, const float* intrinsics,
+                                  const float* extrinsics, float* out, int B, int V, int C, int H, int W, int N,
+                                  pmvs_stream_t stream) {
+  using namespace pmvs;
+  PMVS_REQUIRE(feature_maps && pts && intrinsics && out, "feature_fetch: NULL pointer");
+  PMVS_REQUIRE(B > 0 && V > 0 && C > 0 && H > 1 && W > 1 && N >= 0, "feature_fetch: bad shape");
+  PMVS_REQUIRE((long long)B * V <= 65535, "feature_fetch: B*V too large");
+  if (N == 0) return PMVS_OK;
+  dim3 grid(cdiv(N, 256), B * V);
+  feature_fetch_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(feature_maps, pts, intrinsics, extrinsics, out,
+                                                                    nullptr, V, C, H, W, N);
+  return check_launch("feature_fetch_kernel");
+}
+
+extern "C" int pmvs_feature_fetch_backward(const float* grad_out, const float* pts, const float* intrinsics,
+                                           const float* extrinsics, float* grad_maps, int B, int V, int C, int H,
+                                           int W, int N, pmvs_stream_t stream) {
+  using namespace pmvs;
+  PMVS_REQUIRE(grad_out && pts && intrinsics && grad_maps, "feature_fetch_backward: NULL pointer");
+  PMVS_REQUIRE(B > 0 && V > 0 && C > 0 && H > 1 && W > 1 && N >= 0, "feature_fetch_backward: bad shape");
+  PMVS_REQUIRE((long long)B * V <= 65535, "feature_fetch_backward: B*V too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(grad_maps, 0, (size_t)B * V * C * H * W * sizeof(float), st) != cudaSuccess) {
+    set_error("feature_fetch_backward: memset failed");
+    return PMVS_ERR_CUDA;
+  }
+  if (N == 0) return PMVS_OK;
+  dim3 grid(cdiv(N, 256), B * V);
+  feature_fetch_kernel<true><<<grid, 256, 0, st>>>(nullptr, pts, intrinsics, extrinsics, const_cast<float*>(grad_out),
+                                                   grad_maps, V, C, H, W, N);
+  return check_launch("feature_fetch_backward_kernel");
+}

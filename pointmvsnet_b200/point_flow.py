@@ -1,0 +1,316 @@
+"""PointFlow: the ``point_flow`` closure of the reference (pointmvsnet/model.py:150-295)
+as an nn.Module, executed by libpmvs_b200.so.
+
+One call = one refinement iteration = ~16 kernel launches enqueued by a single C-ABI
+call (``pmvs_point_flow_iter``); ``PointFlowPass`` runs the reference's iteration loop
+(model.py:297-303) and can capture it into a CUDA graph.
+
+The module owns (or shares with a reference ``PointMVSNet``) the sub-modules
+``flow_edge_conv`` and ``flow_mlp`` under the reference's names, so
+``outputs/dtu_wde3/model_pretrained.pth`` loads with no missing hot-path keys.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib, check, stream_ptr, ptr, require_cuda, FlowShape, FlowWeights
+from .networks import EdgeConv, EdgeConvNoC
+from .nn.mlp import SharedMLP
+
+PYR_KEYS = ("conv1", "conv2", "conv3")
+PYR_CH = (16, 32, 64)
+
+
+def _ratio_for(image_scale, is_test):
+    """model.py:231-268: one cloud at scale 0.125, ratio^2 strided sub-clouds otherwise."""
+    if not is_test:
+        return 1
+    if image_scale in (0.125,):
+        return 1
+    if image_scale in (0.25, 0.5, 1.0):
+        return int(image_scale * 8)
+    raise NotImplementedError("point_flow: image_scale %r (reference supports 0.125, 0.25, 0.5, 1.0)" % (image_scale,))
+
+
+class PointFlow(nn.Module):
+    def __init__(self, flow_channels=(64, 64, 16, 1), k=16, flow_edge_conv=None, flow_mlp=None,
+                 update_running_stats=True):
+        super(PointFlow, self).__init__()
+        if k != 16:
+            raise NotImplementedError("PointFlow: k=16 is what the reference hard-wires (model.py:20,23)")
+        if tuple(flow_channels) != (64, 64, 16, 1):
+            raise NotImplementedError("PointFlow: flow_channels (64, 64, 16, 1) (model.py:18)")
+        self.k = k
+        if flow_edge_conv is None:  # model.py:31-39
+            flow_edge_conv = nn.ModuleList([EdgeConvNoC(136, 32), EdgeConv(32, 32), EdgeConv(64, 64)])
+        if flow_mlp is None:  # model.py:40-43
+            flow_mlp = nn.Sequential(SharedMLP(32 + 32 * 2 + 64 * 2, flow_channels[:-1]),
+                                     nn.Conv1d(flow_channels[-2], flow_channels[-1], 1, bias=False))
+        self.flow_edge_conv = flow_edge_conv
+        self.flow_mlp = flow_mlp
+        self.update_running_stats = update_running_stats
+        self._wcache = None
+        self._ws = None
+        self._cl_cache = None
+
+    # ------------------------------------------------------------------ weights
+    EXPECTED_SHAPES = {
+        "flow_edge_conv.0.conv1.weight": (32, 136, 1), "flow_edge_conv.0.conv2.weight": (32, 136, 1),
+        "flow_edge_conv.0.bn.weight": (32,), "flow_edge_conv.0.bn.bias": (32,),
+        "flow_edge_conv.1.conv1.weight": (32, 32, 1), "flow_edge_conv.1.conv2.weight": (32, 32, 1),
+        "flow_edge_conv.1.bn.weight": (64,), "flow_edge_conv.1.bn.bias": (64,),
+        "flow_edge_conv.2.conv1.weight": (64, 64, 1), "flow_edge_conv.2.conv2.weight": (64, 64, 1),
+        "flow_edge_conv.2.bn.weight": (128,), "flow_edge_conv.2.bn.bias": (128,),
+        "flow_mlp.0.0.conv.weight": (64, 224, 1), "flow_mlp.0.0.bn.weight": (64,), "flow_mlp.0.0.bn.bias": (64,),
+        "flow_mlp.0.1.conv.weight": (64, 64, 1), "flow_mlp.0.1.bn.weight": (64,), "flow_mlp.0.1.bn.bias": (64,),
+        "flow_mlp.0.2.conv.weight": (16, 64, 1), "flow_mlp.0.2.bn.weight": (16,), "flow_mlp.0.2.bn.bias": (16,),
+        "flow_mlp.1.weight": (1, 16, 1),
+    }
+
+    def load_reference_state_dict(self, state_dict):
+        """Load the hot-path entries of a reference checkpoint (keys may carry the
+        ``module.`` prefix DataParallel adds, train.py:177).  Unlike the reference's
+        ``strict=False`` load (utils/checkpoint.py:52) every expected key and shape is
+        checked explicitly."""
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        own = self.state_dict()
+        for k, shape in self.EXPECTED_SHAPES.items():
+            if k not in sd:
+                raise KeyError("reference checkpoint lacks hot-path key %s" % k)
+            if tuple(sd[k].shape) != shape:
+                raise ValueError("%s: shape %s, expected %s" % (k, tuple(sd[k].shape), shape))
+        self.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=True)
+        self._wcache = None
+        return self
+
+    def _weights(self, device):
+        # running statistics are passed by pointer on every call and are not part of the key
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._wcache is not None and self._wcache[0] == key:
+            return self._wcache[1], self._wcache[2]
+        keep = []
+
+        def dev(t):
+            t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t
+
+        w = FlowWeights()
+        for l, ec in enumerate(self.flow_edge_conv):
+            w12 = dev(torch.cat([ec.conv1.weight.detach()[:, :, 0], ec.conv2.weight.detach()[:, :, 0]], dim=0))
+            w.ec_w12[l] = ptr(w12)
+            w.ec_gamma[l] = ptr(dev(ec.bn.weight))
+            w.ec_beta[l] = ptr(dev(ec.bn.bias))
+        mlp = self.flow_mlp[0]
+        for l in range(3):
+            w.mlp_w[l] = ptr(dev(mlp[l].conv.weight.detach()[:, :, 0]))
+            w.mlp_gamma[l] = ptr(dev(mlp[l].bn.weight))
+            w.mlp_beta[l] = ptr(dev(mlp[l].bn.bias))
+        w.mlp_w[3] = ptr(dev(self.flow_mlp[1].weight.detach()[:, :, 0]))
+        w.momentum = float(self.flow_edge_conv[0].bn.momentum if self.flow_edge_conv[0].bn.momentum is not None else 0.1)
+        w.eps = float(self.flow_edge_conv[0].bn.eps)
+        self._wcache = (key, w, keep)
+        return w, keep
+
+    def _bn_modules(self):
+        return [ec.bn for ec in self.flow_edge_conv] + [self.flow_mlp[0][l].bn for l in range(3)]
+
+    # ------------------------------------------------------------------ pyramids
+    @staticmethod
+    def pyramids_to_channels_last(feature_pyramids, out=None):
+        """[B,V,C,h,w] (reference layout, model.py:133-148) -> [B,V,h,w,C], once per pass.
+        Tensors that already are channels-last in memory (e.g. produced by a
+        ``channels_last`` ImageConv) are used as they are."""
+        levels = [feature_pyramids[k] for k in PYR_KEYS] if isinstance(feature_pyramids, dict) else list(feature_pyramids)
+        res = []
+        for l, t in enumerate(levels):
+            require_cuda(t)
+            B, V, Cc, h, w = t.shape
+            if Cc != PYR_CH[l]:
+                raise RuntimeError("pyramid level %d must have %d channels, got %d" % (l, PYR_CH[l], Cc))
+            if t.dtype == torch.float32 and t.permute(0, 1, 3, 4, 2).is_contiguous():
+                res.append(t.permute(0, 1, 3, 4, 2))
+                continue
+            src = _lib.f32c(t)
+            dst = out[l] if out is not None else torch.empty(B, V, h, w, Cc, device=t.device, dtype=torch.float32)
+            with torch.cuda.device(t.device):
+                check(lib.pmvs_pyramid_to_channels_last(ptr(src), ptr(dst), B * V, Cc, h, w, stream_ptr()))
+            res.append(dst)
+        return res
+
+    # ------------------------------------------------------------------ shape / workspace
+    @staticmethod
+    def make_shape(B, V, pyr_hw, prev_hw, img_hw, image_scale, is_test):
+        s = FlowShape()
+        s.B, s.V = B, V
+        for l in range(3):
+            s.pyr_h[l], s.pyr_w[l] = pyr_hw[l]
+        s.prev_h, s.prev_w = prev_hw
+        s.flow_h, s.flow_w = int(img_hw[0] * image_scale), int(img_hw[1] * image_scale)  # model.py:154-155
+        s.image_scale = float(image_scale)
+        s.ratio = _ratio_for(image_scale, is_test)
+        s.is_test = 1 if is_test else 0
+        return s
+
+    def _workspace(self, shape, device):
+        need = lib.pmvs_point_flow_workspace_bytes(C.byref(shape))
+        if need == 0:
+            raise RuntimeError("libpmvs_b200: " + lib.pmvs_last_error().decode())
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, device=device, dtype=torch.uint8)
+        return self._ws, need
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, estimated_depth_map, interval, image_scale, it=0, *, feature_pyramids, cam_params_list,
+                mean, std, is_test=True, img_hw=None, pyramids_channels_last=None, out=None):
+        """One refinement iteration (model.py:150-295).
+
+        estimated_depth_map [B,1,hp,wp]; interval [B] (= inter_scale * depth_interval,
+        model.py:301); feature_pyramids: dict conv1/conv2/conv3 -> [B,V,C,h,w] (or the
+        list returned by ``pyramids_to_channels_last`` via ``pyramids_channels_last``);
+        cam_params_list [B,V,2,4,4]; mean/std [B,3].  Returns (flow_result [B,1,h,w],
+        flow_prob [B,5,h,w])."""
+        require_cuda(estimated_depth_map, interval, cam_params_list, mean, std)
+        dev = estimated_depth_map.device
+        if pyramids_channels_last is None:
+            pyramids_channels_last = self.pyramids_to_channels_last(feature_pyramids)
+        pyr = pyramids_channels_last
+        B, V = cam_params_list.shape[:2]
+        pyr_hw = [(int(t.shape[2]), int(t.shape[3])) for t in pyr]
+        if img_hw is None:
+            img_hw = (pyr_hw[0][0] * 2, pyr_hw[0][1] * 2)  # conv1 is at half resolution (networks.py:84-124)
+        depth = _lib.f32c(estimated_depth_map)
+        shape = self.make_shape(B, V, pyr_hw, tuple(depth.shape[2:]), img_hw, image_scale, is_test)
+        ws, need = self._workspace(shape, dev)
+        w, _keep = self._weights(dev)
+        track = self.update_running_stats and self.training
+        bns = self._bn_modules()
+        for l in range(3):
+            w.ec_run_mean[l] = ptr(bns[l].running_mean) if track else None
+            w.ec_run_var[l] = ptr(bns[l].running_var) if track else None
+            w.mlp_run_mean[l] = ptr(bns[3 + l].running_mean) if track else None
+            w.mlp_run_var[l] = ptr(bns[3 + l].running_var) if track else None
+        h, wd = shape.flow_h, shape.flow_w
+        if out is None:
+            depth_out = torch.empty(B, 1, h, wd, device=dev, dtype=torch.float32)
+            prob_out = torch.empty(B, 5, h, wd, device=dev, dtype=torch.float32)
+        else:
+            depth_out, prob_out = out
+        cams = _lib.f32c(cam_params_list)
+        itv = _lib.f32c(interval.reshape(-1))
+        mean_c, std_c = _lib.f32c(mean), _lib.f32c(std)
+        pyr_ptrs = (C.c_void_p * 3)(*[t.data_ptr() for t in pyr])
+        with torch.cuda.device(dev):
+            check(lib.pmvs_point_flow_iter(C.byref(shape), C.byref(w), C.byref(pyr_ptrs), ptr(depth), ptr(cams),
+                                           ptr(itv), ptr(mean_c), ptr(std_c), ptr(depth_out), ptr(prob_out),
+                                           ptr(ws), need, stream_ptr()))
+            if track:
+                for bn in bns:
+                    bn.num_batches_tracked.add_(shape.ratio * shape.ratio)
+        self._last = (shape, ws)
+        return depth_out, prob_out
+
+    # ------------------------------------------------------------------ debugging / parity
+    def debug_stages(self):
+        """Views of the last iteration's workspace in the REFERENCE layouts (test helper):
+        feature [B,136,5,h,w]-equivalent per sub-cloud etc.  Returns a dict of tensors
+        indexed [S, B, ...]."""
+        shape, ws = self._last
+        off = (C.c_size_t * 8)()
+        check(lib.pmvs_point_flow_debug_offsets(C.byref(shape), C.byref(off)))
+        S = shape.ratio * shape.ratio
+        hs, wsub = shape.flow_h // shape.ratio, shape.flow_w // shape.ratio
+        N = 5 * hs * wsub
+        R = S * shape.B * N
+
+        def view(o, cols, dtype=torch.float32):
+            nbytes = R * cols * 4
+            return ws[o:o + nbytes].view(dtype).view(S, shape.B, N, cols)
+
+        return {
+            "feature": view(off[0], 136), "xyz": ws[off[1]:off[1] + R * 12].view(torch.float32).view(S, shape.B, 3, N),
+            "idx": view(off[2], 16, torch.int32), "edge": view(off[3], 224), "h2": view(off[4], 16),
+            "S": S, "hs": hs, "ws": wsub, "N": N,
+        }
+
+
+class PointFlowPass(object):
+    """The iteration loop of the reference (model.py:297-303) over a fixed input shape,
+    optionally captured into a CUDA graph (static input/output buffers)."""
+
+    def __init__(self, point_flow, img_scales=(0.125, 0.25, 0.5), inter_scales=(1.0, 0.75, 0.15), is_test=True):
+        self.pf = point_flow
+        self.img_scales = tuple(img_scales)
+        self.inter_scales = tuple(inter_scales)
+        self.is_test = is_test
+        self.graph = None
+        self.static = None
+
+    def run(self, pyramids, coarse_depth, cam_params_list, depth_interval, mean, std, img_hw, cl_buffers=None,
+            outs=None, intervals=None):
+        pyr_cl = PointFlow.pyramids_to_channels_last(pyramids, out=cl_buffers)
+        depth = coarse_depth
+        results = []
+        for i, (s, isc) in enumerate(zip(self.img_scales, self.inter_scales)):
+            itv = intervals[i] if intervals is not None else depth_interval * isc
+            depth, prob = self.pf(depth, itv, s, i, feature_pyramids=None, cam_params_list=cam_params_list, mean=mean,
+                                  std=std, is_test=self.is_test, img_hw=img_hw, pyramids_channels_last=pyr_cl,
+                                  out=None if outs is None else outs[i])
+            results.append((depth, prob))
+        return results
+
+    def capture(self, example):
+        """Capture one pass on static copies of ``example`` (dict from
+        synthetic.make_pointflow_inputs on the GPU).  Afterwards ``replay(inputs)``
+        copies new inputs into the static buffers and launches the graph."""
+        dev = example["coarse_depth"].device
+        st = {
+            "pyramids": [torch.empty_like(p).copy_(p) for p in example["pyramids"]],
+            "coarse_depth": example["coarse_depth"].clone(),
+            "cam_params_list": example["cam_params_list"].clone(),
+            "depth_interval": example["depth_interval"].clone(),
+            "mean": example["mean"].clone(), "std": example["std"].clone(),
+        }
+        img_hw = example["img_hw"]
+        B = st["coarse_depth"].shape[0]
+        cl = [torch.empty(p.shape[0], p.shape[1], p.shape[3], p.shape[4], p.shape[2], device=dev) for p in st["pyramids"]]
+        outs = []
+        for s in self.img_scales:
+            h, w = int(img_hw[0] * s), int(img_hw[1] * s)
+            outs.append((torch.empty(B, 1, h, w, device=dev), torch.empty(B, 5, h, w, device=dev)))
+        intervals = [torch.empty_like(st["depth_interval"]) for _ in self.inter_scales]
+
+        def body():
+            for i, isc in enumerate(self.inter_scales):
+                torch.mul(st["depth_interval"], isc, out=intervals[i])
+            return self.run(st["pyramids"], st["coarse_depth"], st["cam_params_list"], st["depth_interval"],
+                            st["mean"], st["std"], img_hw, cl_buffers=cl, outs=outs, intervals=intervals)
+
+        # warm-up on a side stream (allocates the workspace, fills the weight cache)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        launches0 = _lib.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        self.launches_per_pass = _lib.launch_count() - launches0
+        self.graph, self.static, self.outs = g, st, outs
+        return self
+
+    def copy_inputs(self, inputs, non_blocking=True):
+        st = self.static
+        for d, s in zip(st["pyramids"], inputs["pyramids"]):
+            d.copy_(s, non_blocking=non_blocking)
+        for k in ("coarse_depth", "cam_params_list", "depth_interval", "mean", "std"):
+            st[k].copy_(inputs[k], non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        return self.outs
