@@ -47,6 +47,13 @@ const char* pmvs_last_error(void);
 /* number of kernels this library has launched since load (all threads, all devices) */
 unsigned long long pmvs_launch_count(void);
 
+/* Per-launch CUDA-event timing for bench.py's roofline: while enabled every kernel launch of
+ * this library is bracketed by two events on its stream (do not enable during graph capture).
+ * pmvs_profile_collect synchronises, writes '\n'-separated kernel names and durations (ms)
+ * for up to max_records launches in launch order, clears the log, returns the count. */
+int pmvs_profile_enable(int on);
+int pmvs_profile_collect(char* names, size_t names_bytes, float* ms, int max_records);
+
 /* ---- a13: gather_knn  (dgcnn_ext.gather_knn_forward/backward, main.cpp:4-5;
  *      GatherKNNForward gather_knn_kernel.cu:25-47, GatherKNNBackward :97-148) -------- */
 /* out[b,c,n,k] = in[b,c,idx[b,n,k]];  in [B,C,N], idx [B,N,K] int64, out [B,C,N,K] */

@@ -19,24 +19,50 @@ def install_as_pointmvsnet(reference_root=None):
 
     With ``reference_root`` (a checkout of callmeray/PointMVSNet) the rest of the
     reference package (model.py, dataset, config ...) is imported from there and only
-    the hot-path modules are replaced; see INTEGRATION.md."""
+    the hot-path modules are replaced, so the unchanged ``pointmvsnet/model.py`` runs on
+    the sm_100a kernels.  Without it, stub parent packages are created and every module
+    this package mirrors is aliased (enough for ``from pointmvsnet.utils.torch_utils
+    import get_knn_3d`` style imports).  See INTEGRATION.md."""
     import importlib
     import sys
-    if reference_root is not None and reference_root not in sys.path:
-        sys.path.insert(0, reference_root)
-    mapping = {
+    import types
+    hot = {
         "pointmvsnet.functions.dgcnn_ext": "pointmvsnet_b200.functions.dgcnn_ext",
         "pointmvsnet.functions.gather_knn": "pointmvsnet_b200.functions.gather_knn",
         "pointmvsnet.utils.feature_fetcher": "pointmvsnet_b200.utils.feature_fetcher",
         "pointmvsnet.utils.torch_utils": "pointmvsnet_b200.utils.torch_utils",
     }
-    for ref_name, ours in mapping.items():
-        sys.modules[ref_name] = importlib.import_module(ours)
+    extra = {
+        "pointmvsnet.functions.functions": "pointmvsnet_b200.functions.functions",
+        "pointmvsnet.networks": "pointmvsnet_b200.networks",
+        "pointmvsnet.nn.conv": "pointmvsnet_b200.nn.conv",
+        "pointmvsnet.nn.mlp": "pointmvsnet_b200.nn.mlp",
+        "pointmvsnet.nn.init": "pointmvsnet_b200.nn.init",
+    }
     if reference_root is not None:
+        if reference_root not in sys.path:
+            sys.path.insert(0, reference_root)
         import pointmvsnet.functions as pf  # the reference package itself
+        for ref_name, ours in hot.items():
+            sys.modules[ref_name] = importlib.import_module(ours)
         pf.dgcnn_ext = sys.modules["pointmvsnet.functions.dgcnn_ext"]
         import pointmvsnet.networks as ref_networks
         from pointmvsnet_b200 import networks as ours_networks
         ref_networks.EdgeConv = ours_networks.EdgeConv
         ref_networks.EdgeConvNoC = ours_networks.EdgeConvNoC
         ref_networks.gather_knn = sys.modules["pointmvsnet.functions.gather_knn"].gather_knn
+        return
+    mapping = dict(hot)
+    mapping.update(extra)
+    for parent in ("pointmvsnet", "pointmvsnet.functions", "pointmvsnet.utils", "pointmvsnet.nn"):
+        if parent not in sys.modules:
+            stub = types.ModuleType(parent)
+            stub.__path__ = []
+            sys.modules[parent] = stub
+    for ref_name, ours in mapping.items():
+        mod = importlib.import_module(ours)
+        sys.modules[ref_name] = mod
+        parent, _, leaf = ref_name.rpartition(".")
+        setattr(sys.modules[parent], leaf, mod)
+    for parent in ("pointmvsnet.functions", "pointmvsnet.utils", "pointmvsnet.nn"):
+        setattr(sys.modules["pointmvsnet"], parent.rpartition(".")[2], sys.modules[parent])

@@ -52,6 +52,8 @@ P, I, LL, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _sig("pmvs_version", I, [])
 _sig("pmvs_last_error", C.c_char_p, [])
 _sig("pmvs_launch_count", C.c_ulonglong, [])
+_sig("pmvs_profile_enable", I, [I])
+_sig("pmvs_profile_collect", I, [C.c_char_p, C.c_size_t, P, I])
 _sig("pmvs_gather_knn_forward", I, [P, P, P, I, I, I, I, P])
 _sig("pmvs_gather_knn_backward", I, [P, P, P, I, I, I, I, P])
 _sig("pmvs_knn3d", I, [P, P, P, I, I, I, I, I, I, P])
@@ -67,7 +69,7 @@ _sig("pmvs_pyramid_to_channels_last", I, [P, P, I, I, I, I, P])
 _sig("pmvs_point_flow_debug_offsets", I, [C.POINTER(FlowShape), C.POINTER(C.c_size_t * 8)])
 
 EXPORTED = [
-    "pmvs_version", "pmvs_last_error", "pmvs_launch_count", "pmvs_gather_knn_forward",
+    "pmvs_version", "pmvs_last_error", "pmvs_launch_count", "pmvs_profile_enable", "pmvs_profile_collect", "pmvs_gather_knn_forward",
     "pmvs_gather_knn_backward", "pmvs_knn3d", "pmvs_feature_fetch", "pmvs_feature_fetch_backward",
     "pmvs_transpose", "pmvs_idx64_to_idx32", "pmvs_edgeconv_pm", "pmvs_point_flow_workspace_bytes",
     "pmvs_point_flow_iter", "pmvs_pyramid_to_channels_last", "pmvs_point_flow_debug_offsets",
@@ -104,3 +106,16 @@ def f32c(t):
 
 def launch_count():
     return int(lib.pmvs_launch_count())
+
+
+def profile_enable(on):
+    lib.pmvs_profile_enable(1 if on else 0)
+
+
+def profile_collect(max_records=65536):
+    """-> list of (kernel name, milliseconds) in launch order"""
+    names = C.create_string_buffer(max_records * 24)
+    ms = (C.c_float * max_records)()
+    n = lib.pmvs_profile_collect(names, len(names), C.cast(ms, C.c_void_p), max_records)
+    nm = names.value.decode().split("\n")[:n]
+    return [(nm[i], float(ms[i])) for i in range(n)]

@@ -1,8 +1,11 @@
 // C-ABI glue: error state, launch counter, small layout kernels, the gather_knn operator
 // (reference functions/csrc/gather_knn_kernel.cu) and the PointFlow iteration driver
 // (reference model.py:150-295).
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -18,6 +21,33 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// ---- optional per-launch event timing ------------------------------------------------------
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<int> g_prof_on{0};
+static thread_local int g_prof_open = -1;
+
+void prof_begin(const char* what, cudaStream_t st) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r;
+  r.name = what;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  g_prof_open = (int)g_prof.size() - 1;
+}
+void prof_end(cudaStream_t st) {
+  if (g_prof_open < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_open < (int)g_prof.size()) cudaEventRecord(g_prof[g_prof_open].b, st);
+  g_prof_open = -1;
+}
 
 // ---------------------------------------------------------------------------------------
 // batched transpose  in [batch, R, C] -> out [batch, C, R]
@@ -45,8 +75,9 @@ int launch_transpose(const float* in, float* out, int batch, int R, int C, cudaS
   PMVS_REQUIRE(in && out && batch > 0 && R > 0 && C > 0, "transpose: bad arguments");
   PMVS_REQUIRE(batch <= 65535 && cdiv(R, 32) <= 65535, "transpose: shape too large");
   dim3 grid(cdiv(C, 32), cdiv(R, 32), batch);
+  prof_begin("transpose", st);
   transpose_kernel<<<grid, 256, 0, st>>>(in, out, R, C);
-  return check_launch("transpose_kernel");
+  return check_launch("transpose_kernel", st);
 }
 
 __global__ void idx_convert_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, long long n) {
@@ -144,6 +175,37 @@ extern "C" int pmvs_version(void) { return 100; }
 extern "C" const char* pmvs_last_error(void) { return g_err; }
 extern "C" unsigned long long pmvs_launch_count(void) { return g_launches.load(); }
 
+extern "C" int pmvs_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return PMVS_OK;
+}
+
+extern "C" int pmvs_profile_collect(char* names, size_t names_bytes, float* ms, int max_records) {
+  // synchronises on every recorded event; returns the number of records written
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  size_t pos = 0;
+  if (names && names_bytes) names[0] = 0;
+  for (auto& r : g_prof) {
+    float t = -1.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess) cudaEventElapsedTime(&t, r.a, r.b);
+    if (n < max_records && ms && names) {
+      const size_t len = strlen(r.name);
+      if (pos + len + 2 < names_bytes) {
+        memcpy(names + pos, r.name, len);
+        pos += len;
+        names[pos++] = '\n';
+        names[pos] = 0;
+        ms[n++] = t;
+      }
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return n;
+}
+
 extern "C" int pmvs_transpose(const float* in, float* out, int batch, int R, int C, pmvs_stream_t stream) {
   return launch_transpose(in, out, batch, R, C, (cudaStream_t)stream);
 }
@@ -163,10 +225,10 @@ extern "C" int pmvs_idx64_to_idx32(const int64_t* in, int32_t* out, long long n,
 
 extern "C" int pmvs_gather_knn_forward(const float* input, const int64_t* index, float* output, int B, int C, int N,
                                        int K, pmvs_stream_t stream) {
-  PMVS_REQUIRE(input && index && output, "gather_knn_forward: NULL pointer");
   PMVS_REQUIRE(B >= 0 && C >= 0 && N >= 0 && K >= 0, "gather_knn_forward: negative size");
   const long long total = (long long)B * C * N * K;
-  if (total == 0) return PMVS_OK;
+  if (total == 0) return PMVS_OK;  // empty input: nothing to do (pointers may be NULL)
+  PMVS_REQUIRE(input && index && output, "gather_knn_forward: NULL pointer");
   const int grid = (int)std::min<long long>(cdiv(total, 256), 148 * 16);
   gather_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(input, index, output, C, N, K, total);
   return check_launch("gather_fwd_kernel");
@@ -174,8 +236,9 @@ extern "C" int pmvs_gather_knn_forward(const float* input, const int64_t* index,
 
 extern "C" int pmvs_gather_knn_backward(const float* grad_output, const int64_t* index, float* grad_input, int B,
                                         int C, int N, int K, pmvs_stream_t stream) {
-  PMVS_REQUIRE(grad_output && index && grad_input, "gather_knn_backward: NULL pointer");
   PMVS_REQUIRE(B >= 0 && C >= 0 && N >= 0 && K >= 0, "gather_knn_backward: negative size");
+  if ((long long)B * C * N == 0) return PMVS_OK;
+  PMVS_REQUIRE(grad_output && index && grad_input, "gather_knn_backward: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if ((long long)B * C * N > 0 &&
       cudaMemsetAsync(grad_input, 0, (size_t)B * C * N * sizeof(float), st) != cudaSuccess) {

@@ -13,13 +13,19 @@ namespace pmvs {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
-inline int check_launch(const char* what) {
+// optional per-launch CUDA-event timing (pmvs_profile_enable): prof_begin records an event
+// on `st` before the launch, check_launch records the matching one after it.
+void prof_begin(const char* what, cudaStream_t st);
+void prof_end(cudaStream_t st);
+
+inline int check_launch(const char* what, cudaStream_t st = nullptr) {
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cudaGetLastError();
     set_error("%s: %s", what, cudaGetErrorString(e));
     return PMVS_ERR_CUDA;
   }
+  prof_end(st);
   count_launch();
   return PMVS_OK;
 }

@@ -181,6 +181,16 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   PMVS_REQUIRE(a.ldx % 4 == 0 && a.ldy % 4 == 0, "gemm: row strides must be multiples of 4 floats");
   PMVS_REQUIRE(a.groups <= 65535, "gemm: too many groups");
   const int tiles = cdiv(a.rows_per_group, G_BM);
+  static const char* const names[] = {"gemm_136x64", "gemm_32x64", "gemm_64x128", "gemm_224x64",
+                                      "gemm_64x64", "gemm_64x16", "gemm_other"};
+  int ni = 6;
+  if (a.cin == 136 && a.cout == 64) ni = 0;
+  else if (a.cin == 32 && a.cout == 64) ni = 1;
+  else if (a.cin == 64 && a.cout == 128) ni = 2;
+  else if (a.cin == 224 && a.cout == 64) ni = 3;
+  else if (a.cin == 64 && a.cout == 64) ni = 4;
+  else if (a.cin == 64 && a.cout == 16) ni = 5;
+  prof_begin(names[ni], st);
   if (a.cout <= 16) {
     dim3 grid(tiles, a.groups, cdiv(a.cout, 16));
     gemm_kernel<16><<<grid, G_THREADS, 0, st>>>(a);
@@ -188,7 +198,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     dim3 grid(tiles, a.groups, cdiv(a.cout, 64));
     gemm_kernel<64><<<grid, G_THREADS, 0, st>>>(a);
   }
-  return check_launch("gemm_kernel");
+  return check_launch("gemm_kernel", st);
 }
 
 // =======================================================================================
@@ -312,6 +322,9 @@ static int launch_edge(const EdgeArgs& a, cudaStream_t st) {
   PMVS_REQUIRE(a.groups <= 65535, "edgeconv: too many groups");
   PMVS_REQUIRE(a.rows_per_group % a.N == 0, "edgeconv: rows_per_group must be a multiple of N");
   dim3 grid(cdiv(a.rows_per_group, E_PTS_PER_BLOCK), a.groups);
+  static const char* const names[2][4] = {{"edge_stats_16", "edge_stats_32", "edge_stats_64", "edge_stats_128"},
+                                          {"edge_apply_16", "edge_apply_32", "edge_apply_64", "edge_apply_128"}};
+  prof_begin(names[APPLY ? 1 : 0][a.cout == 16 ? 0 : (a.cout == 32 ? 1 : (a.cout == 64 ? 2 : 3))], st);
   switch (a.cout) {
     case 16: edge_kernel<16, APPLY><<<grid, E_THREADS, 0, st>>>(a); break;
     case 32: edge_kernel<32, APPLY><<<grid, E_THREADS, 0, st>>>(a); break;
@@ -321,7 +334,7 @@ static int launch_edge(const EdgeArgs& a, cudaStream_t st) {
       set_error("edgeconv: unsupported out_channels=%d (supported: 16, 32, 64, 128)", a.cout);
       return PMVS_ERR_ARG;
   }
-  return check_launch(APPLY ? "edge_apply_kernel" : "edge_stats_kernel");
+  return check_launch(APPLY ? "edge_apply_kernel" : "edge_stats_kernel", st);
 }
 int launch_edge_stats(const EdgeArgs& a, cudaStream_t st) { return launch_edge<false>(a, st); }
 int launch_edge_apply(const EdgeArgs& a, cudaStream_t st) { return launch_edge<true>(a, st); }
@@ -401,8 +414,9 @@ __global__ void __launch_bounds__(256) flow_head_kernel(const HeadArgs a) {
 int launch_flow_head(const HeadArgs& a, cudaStream_t st) {
   const int P = (a.h / a.ratio) * (a.w / a.ratio);
   dim3 grid(cdiv((long long)a.B * P, 256), a.S);
+  prof_begin("flow_head", st);
   flow_head_kernel<<<grid, 256, 0, st>>>(a);
-  return check_launch("flow_head_kernel");
+  return check_launch("flow_head_kernel", st);
 }
 
 // =======================================================================================
@@ -428,8 +442,9 @@ __global__ void bn_running_update_kernel(const RunUpdateBatch rb) {
 }
 int launch_bn_running_update(const RunUpdateBatch& rb, cudaStream_t st) {
   if (rb.n == 0) return PMVS_OK;
+  prof_begin("bn_running_update", st);
   bn_running_update_kernel<<<rb.n, 128, 0, st>>>(rb);
-  return check_launch("bn_running_update_kernel");
+  return check_launch("bn_running_update_kernel", st);
 }
 
 }  // namespace pmvs

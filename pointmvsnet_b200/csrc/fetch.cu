@@ -396,14 +396,16 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
 
 int launch_cam_setup(const float* cam_params, const float* interval, const float* mean, const float* stdv,
                      float* blocks, int B, int V, float kscale, cudaStream_t st) {
+  prof_begin("cam_setup", st);
   cam_setup_kernel<<<cdiv(B, 32), 32, 0, st>>>(cam_params, interval, mean, stdv, blocks, B, V, kscale);
-  return check_launch("cam_setup_kernel");
+  return check_launch("cam_setup_kernel", st);
 }
 
 int launch_fused_fetch(const FusedFetchParams& p, cudaStream_t st) {
   dim3 grid(cdiv((long long)p.h * p.w, FETCH_WARPS), p.B);
+  prof_begin("fused_fetch", st);
   fused_fetch_kernel<<<grid, FETCH_WARPS * 32, 0, st>>>(p);
-  return check_launch("fused_fetch_kernel");
+  return check_launch("fused_fetch_kernel", st);
 }
 
 size_t cam_block_bytes(int B, int V) { return (size_t)B * cam_block_floats(V) * sizeof(float); }

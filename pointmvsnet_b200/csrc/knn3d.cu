@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(KNN_TX* KNN_TY* KNN_TD)
   // candidate id -> linear index with the reference's global clamp (torch_utils.py:51-59)
   const long long n = (long long)z * HW + (long long)y * W + x;
   IdxT* dst = idx_out + ((long long)cloud * DHW + n) * K;
-  IdxT vals[K];
+  __align__(16) IdxT vals[K];
 #pragma unroll
   for (int p = 0; p < K; ++p) {
     const int j = bi[p];
@@ -123,11 +123,12 @@ static int launch_ks_k(const float* xyz, int64_t* idx64, int32_t* idx32, int clo
   const int dtiles = cdiv(D, KNN_TD);
   dim3 block(KNN_TX, KNN_TY, KNN_TD);
   dim3 grid(cdiv(W, KNN_TX), cdiv(H, KNN_TY), clouds * dtiles);
+  prof_begin("knn3d", st);
   if (idx32)
     knn3d_kernel<KS, K, int32_t><<<grid, block, 0, st>>>(xyz, idx32, D, H, W, dtiles);
   else
     knn3d_kernel<KS, K, int64_t><<<grid, block, 0, st>>>(xyz, idx64, D, H, W, dtiles);
-  return check_launch("knn3d_kernel");
+  return check_launch("knn3d_kernel", st);
 }
 
 template <int KS>

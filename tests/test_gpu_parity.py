@@ -1,0 +1,374 @@
+"""GPU parity tests: the CUDA path (through the C ABI / Python mirror) against the CPU oracle
+and the committed golden vectors.  Tolerances (fp32, stated per stage; measured errors on
+B200 are ~10x smaller, see profiles/parity_r01.md):
+
+  gather_knn fwd/bwd ............ bit exact
+  FeatureFetcher vs oracle ...... atol 1e-5 (same op sequence; measured 0)
+  kNN indices ................... bit exact on EVERY point (canonical tie order on both sides)
+  variance features ............. atol 3e-5 + rtol 1e-5   (values up to ~6; cancellation)
+  normalised xyz ................ atol 1e-6
+  EdgeConv / EdgeConvNoC ........ atol 2e-5 + rtol 1e-4   (fp32 FMA order)
+  depth after one iteration ..... atol 5e-4 mm (< 5e-5 * interval; depths ~650 mm, ulp 6e-5)
+  flow probabilities ............ atol 5e-5
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pointflow_oracle as O
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pf(weights):
+    from pointmvsnet_b200.point_flow import PointFlow
+    pf = PointFlow().to(DEV)
+    pf.load_reference_state_dict(weights)
+    pf.train()
+    return pf
+
+
+def sub_to_ref(t, S, B, M, hs, ws, r):
+    Cc = t.shape[-1]
+    x = t.view(r, r, B, M, hs, ws, Cc).permute(2, 6, 3, 4, 0, 5, 1)
+    return x.reshape(B, Cc, M, hs * r, ws * r)
+
+
+def test_native_library_is_loaded():
+    from pointmvsnet_b200 import _lib
+    assert _lib.lib.pmvs_version() >= 100
+    maps = open("/proc/self/maps").read()
+    assert "libpmvs_b200.so" in maps
+
+
+def test_gather_knn_golden_forward_backward():
+    from pointmvsnet_b200.functions.gather_knn import gather_knn
+    g = load_golden("gather_knn.npz")
+    f = g["feature"].to(DEV).requires_grad_(True)
+    out = gather_knn(f, g["index"].to(DEV))
+    assert torch.equal(out.cpu(), g["out"])
+    out.backward(g["grad_out"].to(DEV))
+    assert torch.allclose(f.grad.cpu(), g["grad_in"], atol=1e-6)
+    # reference's own inline test (gather_knn.py:27-56): equals torch.gather, grads of ones
+    torch.manual_seed(1)
+    feat = torch.rand(2, 4, 5, device=DEV)
+    idx = torch.randint(0, 5, [2, 5, 3], device=DEV)
+    a = feat.clone().requires_grad_(True)
+    b = feat.clone().requires_grad_(True)
+    ga = torch.gather(a.unsqueeze(2).expand(2, 4, 5, 5), 3, idx.unsqueeze(1).expand(2, 4, 5, 3))
+    gb = gather_knn(b, idx)
+    assert torch.equal(ga, gb)
+    ga.backward(torch.ones_like(ga))
+    gb.backward(torch.ones_like(gb))
+    assert torch.allclose(a.grad, b.grad)
+
+
+def test_gather_knn_error_behaviour():
+    from pointmvsnet_b200.functions import dgcnn_ext
+    with pytest.raises(RuntimeError):
+        dgcnn_ext.gather_knn_forward(torch.zeros(1, 2, 3), torch.zeros(1, 3, 2, dtype=torch.long, device=DEV))
+    with pytest.raises(RuntimeError):
+        dgcnn_ext.gather_knn_forward(torch.zeros(1, 2, 3, device=DEV), torch.zeros(2, 3, 2, dtype=torch.long, device=DEV))
+    # empty input
+    out = dgcnn_ext.gather_knn_forward(torch.zeros(1, 2, 0, device=DEV), torch.zeros(1, 0, 4, dtype=torch.long, device=DEV))
+    assert tuple(out.shape) == (1, 2, 0, 4)
+
+
+def test_feature_fetch_known_answer_and_oracle():
+    from pointmvsnet_b200.utils.feature_fetcher import FeatureFetcher
+    g = load_golden("fetch_known_answer.npz")
+    H, W = [int(v) for v in g["hw"]]
+    y0, y1, x0, x1 = [int(v) for v in g["crop"]]
+    B, V, Cc = g["feats"].shape[:3]
+    feats = torch.zeros(B, V, Cc, H, W)
+    feats[:, :, :, y0:y1, x0:x1] = g["feats"]
+    ff = FeatureFetcher()
+    out = ff(feats.to(DEV), g["pts"].to(DEV), g["K"].to(DEV), g["E"].to(DEV)).cpu()
+    # the reference's criterion (feature_fetcher.py:97): allclose(gathered, truth, rtol=1e-2)
+    # the reference's criterion is allclose(gathered, truth, rtol=1e-2) (feature_fetcher.py:97);
+    # features are in [0,1] and the reference run itself is 8e-5 off the analytic value
+    assert np.allclose(out[:, 0, :, 0].numpy(), g["truth"].numpy(), rtol=1e-2, atol=5e-4)
+    assert torch.allclose(out[:, 0], g["out_view0"], atol=5e-4)
+    # random points incl. out-of-image ones (zeros padding) vs the oracle, and E=None
+    gen = torch.Generator().manual_seed(5)
+    fm = torch.randn(2, 3, 8, 12, 20, generator=gen)
+    pts = torch.randn(2, 3, 700, generator=gen) * torch.tensor([60., 60., 30.]).view(1, 3, 1) + \
+        torch.tensor([0., 0., 650.]).view(1, 3, 1)
+    from pointmvsnet_b200.synthetic import make_cameras
+    cams = make_cameras(2, 3, 96, 160, 48)
+    K = cams[:, :, 1, :3, :3].clone()
+    K[:, :, :2] *= 0.125
+    E = cams[:, :, 0, :3, :4].contiguous()
+    ref = O.feature_fetch(fm, pts, K, E)
+    got = ff(fm.to(DEV), pts.to(DEV), K.to(DEV), E.to(DEV)).cpu()
+    assert (ref == 0).any() and (ref != 0).any()
+    assert torch.allclose(got, ref, atol=1e-5)
+    cam_pts = torch.randn(2, 3, 50, generator=gen) + torch.tensor([0., 0., 5.]).view(1, 3, 1)
+    K2 = torch.tensor([[8., 0, 10], [0, 8., 6], [0, 0, 1]]).view(1, 1, 3, 3).expand(2, 3, 3, 3).contiguous()
+    assert torch.allclose(ff(fm.to(DEV), cam_pts.to(DEV), K2.to(DEV), None).cpu(),
+                          O.feature_fetch(fm, cam_pts, K2, None), atol=1e-5)
+
+
+def test_feature_fetch_backward_matches_autograd_of_oracle():
+    from pointmvsnet_b200.utils.feature_fetcher import FeatureFetcher
+    gen = torch.Generator().manual_seed(8)
+    fm = torch.randn(1, 2, 4, 9, 11, generator=gen)
+    pts = torch.randn(1, 3, 60, generator=gen) + torch.tensor([0., 0., 6.]).view(1, 3, 1)
+    K = torch.tensor([[9., 0, 5], [0, 9., 4], [0, 0, 1]]).view(1, 1, 3, 3).expand(1, 2, 3, 3).contiguous()
+    a = fm.clone().requires_grad_(True)
+    O.feature_fetch(a, pts, K, None).pow(2).sum().backward()
+    b = fm.clone().to(DEV).requires_grad_(True)
+    FeatureFetcher()(b, pts.to(DEV), K.to(DEV), None).pow(2).sum().backward()
+    assert torch.allclose(b.grad.cpu(), a.grad, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape,ks,k", [((2, 3, 5, 20, 36), 5, 16), ((1, 3, 5, 9, 33), 5, 16),
+                                        ((1, 3, 7, 6, 5), 3, 8), ((1, 3, 5, 8, 16), 5, 20),
+                                        ((1, 3, 1, 1, 1), 3, 4), ((3, 3, 12, 7, 40), 5, 32)])
+def test_knn_bit_exact_vs_oracle(shape, ks, k):
+    """Includes ragged tiles, D not a multiple of the depth tile, a single-point cloud and
+    tie-heavy inputs (duplicated points): canonical order must match everywhere."""
+    from pointmvsnet_b200.utils.torch_utils import get_knn_3d
+    gen = torch.Generator().manual_seed(11)
+    xyz = torch.randn(*shape, generator=gen)
+    xyz[:, :, :, ::3] = xyz[:, :, :, 0:1].clone()  # exact duplicates -> exact ties
+    want = O.knn3d(xyz, ks, k)
+    got = get_knn_3d(xyz.to(DEV), ks, k)
+    assert got.dtype == torch.int64 and tuple(got.shape) == tuple(want.shape)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_knn_golden_reference_clouds():
+    """Against get_knn_3d of the reference itself (tests/golden/stages_small.npz): exact on
+    tie-free points, equal distance multiset elsewhere (torch.topk tie order is
+    implementation defined; rule from SURVEY.md section 8c)."""
+    from pointmvsnet_b200.utils.torch_utils import get_knn_3d
+    st = load_golden("stages_small.npz")
+    for tag in ("it1", "it2"):
+        xyz, ref_idx = st[tag + "_xyz"], st[tag + "_knn"]
+        B, _, D, H, W = xyz.shape
+        got = get_knn_3d(xyz.to(DEV), 5, 16).cpu()
+        dist2 = O.knn3d_dist2(xyz, 5)
+        srt = torch.sort(dist2, dim=1, stable=True).values
+        tie_free = (srt[:, 1:17] != srt[:, :16]).all(dim=1)
+        assert torch.equal(got[tie_free], ref_idx[tie_free])
+        rc, gc = O.idx_to_candidates(ref_idx, D, H, W), O.idx_to_candidates(got, D, H, W)
+        ok = ((rc >= 0) & (gc >= 0)).all(dim=2)
+        pr = torch.gather(dist2, 1, rc.clamp(min=0).permute(0, 2, 1)).sort(dim=1).values
+        pg = torch.gather(dist2, 1, gc.clamp(min=0).permute(0, 2, 1)).sort(dim=1).values
+        assert torch.equal(pr.permute(0, 2, 1)[ok], pg.permute(0, 2, 1)[ok])
+
+
+def test_knn_errors():
+    from pointmvsnet_b200.utils.torch_utils import get_knn_3d
+    with pytest.raises(RuntimeError):
+        get_knn_3d(torch.zeros(1, 3, 5, 4, 4, device=DEV), 5, 17)
+    with pytest.raises(RuntimeError):
+        get_knn_3d(torch.zeros(1, 3, 5, 4, 4, device=DEV), 7, 16)
+
+
+def test_edgeconv_modules_vs_reference_stage_tensors(golden_params):
+    from pointmvsnet_b200.networks import EdgeConv, EdgeConvNoC
+    st = load_golden("stages_small.npz")
+    p = golden_params
+    for tag in ("it1", "it2"):
+        x = st[tag + "_feature"].to(DEV)
+        idx = st[tag + "_knn"].to(DEV)
+        mods = [EdgeConvNoC(136, 32), EdgeConv(32, 32), EdgeConv(64, 64)]
+        with torch.no_grad():
+            for l, m in enumerate(mods):
+                m.conv1.weight.copy_(p["ec%d_w1" % l]); m.conv2.weight.copy_(p["ec%d_w2" % l])
+                m.bn.weight.copy_(p["ec%d_gamma" % l]); m.bn.bias.copy_(p["ec%d_beta" % l])
+                m.to(DEV).train()
+                x = m(x, idx)
+                ref = st[tag + "_ec%d_out" % l]
+                assert torch.allclose(x.cpu(), ref, atol=2e-5, rtol=1e-4), (tag, l, (x.cpu() - ref).abs().max())
+
+
+def test_edgeconv_batch_stats_cover_batch_running_stats_and_eval_mode():
+    """B=2 (BN statistics span the batch), running-stat side effect equals nn.BatchNorm2d's,
+    eval mode uses running statistics, neighbour order does not matter."""
+    from pointmvsnet_b200.networks import EdgeConv
+    gen = torch.Generator().manual_seed(21)
+    B, Cin, Cout, N, K = 2, 32, 32, 300, 16
+    x = torch.randn(B, Cin, N, generator=gen)
+    idx = torch.randint(0, N, (B, N, K), generator=gen)
+    m = EdgeConv(Cin, Cout)
+    with torch.no_grad():
+        m.bn.weight.uniform_(0.5, 1.5); m.bn.bias.uniform_(-0.2, 0.2)
+    ref_bn = torch.nn.BatchNorm2d(2 * Cout)
+    ref_bn.load_state_dict(m.bn.state_dict())
+    w1, w2 = m.conv1.weight.detach().clone(), m.conv2.weight.detach().clone()
+    want = O.edge_conv(x, idx, w1, w2, m.bn.weight.detach(), m.bn.bias.detach(), True)
+    # reference side effect on running stats: feed the same [B,2C,N,K] tensor to nn.BatchNorm2d
+    local, edge = O.conv1x1(x, w1), O.conv1x1(x, w2)
+    nb = O.gather_knn(edge, idx)
+    cen = local.unsqueeze(-1).expand(-1, -1, -1, K)
+    ref_bn.train()
+    ref_bn(torch.cat([cen, nb - cen], dim=1))
+    m = m.to(DEV).train()
+    with torch.no_grad():
+        got = m(x.to(DEV), idx.to(DEV))
+        assert torch.allclose(got.cpu(), want, atol=2e-5, rtol=1e-4)
+        assert torch.allclose(m.bn.running_mean.cpu(), ref_bn.running_mean, atol=1e-6)
+        assert torch.allclose(m.bn.running_var.cpu(), ref_bn.running_var, atol=1e-6, rtol=1e-5)
+        assert int(m.bn.num_batches_tracked) == 1
+        perm = torch.randperm(K, generator=gen)
+        got_p = m(x.to(DEV), idx[:, :, perm].to(DEV))
+        assert torch.allclose(got_p, got, atol=1e-5)
+        m.eval()
+        ref_bn.eval()
+        want_eval = torch.relu(ref_bn(torch.cat([cen, nb - cen], dim=1))).mean(dim=3)
+        # our module saw one more train step than ref_bn; align the statistics first
+        m.bn.load_state_dict(ref_bn.state_dict())
+        got_eval = m(x.to(DEV), idx.to(DEV))
+        assert torch.allclose(got_eval.cpu(), want_eval, atol=2e-5, rtol=1e-4)
+    with pytest.raises(NotImplementedError):
+        m.train()
+        m(x.to(DEV), idx.to(DEV))  # grad enabled: forward-only operator refuses
+
+
+def _run_iteration(pf, cpu, depth, scale, isc, it, params, is_test=True):
+    with torch.no_grad():
+        res, prob, stg = O.point_flow(depth, isc * cpu["depth_interval"], scale, cpu["pyramids"],
+                                      cpu["cam_params_list"], cpu["mean"], cpu["std"], cpu["img_hw"], params,
+                                      is_test=is_test, return_stages=True)
+        d_gpu, p_gpu = pf(depth.to(DEV), (isc * cpu["depth_interval"]).to(DEV), scale, it,
+                          feature_pyramids=[p.to(DEV) for p in cpu["pyramids"]],
+                          cam_params_list=cpu["cam_params_list"].to(DEV), mean=cpu["mean"].to(DEV),
+                          std=cpu["std"].to(DEV), img_hw=cpu["img_hw"], is_test=is_test)
+    return res, prob, stg, d_gpu.cpu(), p_gpu.cpu()
+
+
+def _check_stages(pf, stg, B):
+    dbg = pf.debug_stages()
+    S, hs, ws = dbg["S"], dbg["hs"], dbg["ws"]
+    r = int(round(S ** 0.5))
+    feat = sub_to_ref(dbg["feature"].cpu(), S, B, 5, hs, ws, r)
+    assert torch.allclose(feat[:, :112], stg["feature"][:, :112], atol=3e-5, rtol=1e-5)
+    assert torch.allclose(feat[:, 112:], stg["feature"][:, 112:], atol=1e-6)
+    xyz = sub_to_ref(dbg["xyz"].permute(0, 1, 3, 2).contiguous().cpu(), S, B, 5, hs, ws, r)
+    assert torch.allclose(xyz, stg["xyz"], atol=1e-6)
+    return dbg
+
+
+def test_point_flow_iterations_vs_oracle_golden_inputs(golden_weights, golden_params):
+    """All three iterations on the inputs of the reference forward (pass_small.npz); each
+    iteration starts from the oracle's previous depth so stages see identical inputs."""
+    gp = load_golden("pass_small.npz")
+    H, W = [int(v) for v in gp["img_hw"]]
+    cpu = {"pyramids": [gp["conv1"], gp["conv2"], gp["conv3"]], "cam_params_list": gp["cams"], "mean": gp["mean"],
+           "std": gp["std"], "img_hw": (H, W), "depth_interval": gp["cams"][:, 0, 1, 3, 1]}
+    pf = _pf(golden_weights)
+    depth = gp["coarse_depth"]
+    for it, (s, isc) in enumerate(zip((0.125, 0.25, 0.5), (1.0, 0.75, 0.15))):
+        res, prob, stg, d_gpu, p_gpu = _run_iteration(pf, cpu, depth, s, isc, it, golden_params)
+        dbg = _check_stages(pf, stg, 1)
+        assert torch.allclose(d_gpu, res, atol=5e-4, rtol=0), (it, (d_gpu - res).abs().max())
+        assert torch.allclose(p_gpu, prob, atol=5e-5, rtol=0)
+        depth = res
+
+
+def test_point_flow_batch2_train_branch_and_5_views(golden_params):
+    """B=2 (BN statistics span the batch, per-sample interval), V=5, and the train branch
+    (is_test=False: K scaled by 4*image_scale, one cloud, model.py:162-163,271-293)."""
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    from tests.conftest import load_golden as lg
+    cpu = make_pointflow_inputs(64, 128, 5, 2, 48, seed=9)
+    cpu["depth_interval"] = cpu["depth_interval"] * torch.tensor([1.0, 0.8])
+    pf = _pf(lg("flow_weights.npz"))
+    res, prob, stg, d_gpu, p_gpu = _run_iteration(pf, cpu, cpu["coarse_depth"], 0.25, 0.75, 1, golden_params)
+    _check_stages(pf, stg, 2)
+    assert torch.allclose(d_gpu, res, atol=5e-4, rtol=0)
+    assert torch.allclose(p_gpu, prob, atol=5e-5, rtol=0)
+    # train branch: cameras at 1/4 resolution
+    cpu_t = make_pointflow_inputs(64, 128, 3, 1, 48, seed=10)
+    cpu_t["cam_params_list"][:, :, 1, :2, :3] /= 4.0
+    res, prob, stg, d_gpu, p_gpu = _run_iteration(pf, cpu_t, cpu_t["coarse_depth"], 0.25, 0.375, 1, golden_params,
+                                                  is_test=False)
+    assert pf.debug_stages()["S"] == 1
+    assert torch.allclose(d_gpu, res, atol=5e-4, rtol=0)
+    assert torch.allclose(p_gpu, prob, atol=5e-5, rtol=0)
+
+
+def test_point_flow_running_stats_and_graph_replay(golden_weights, golden_params):
+    """BN running statistics after a 4-sub-cloud iteration equal 4 sequential nn.BatchNorm
+    updates; a captured CUDA graph of the whole pass reproduces the eager pass."""
+    from pointmvsnet_b200.point_flow import PointFlowPass
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    cpu = make_pointflow_inputs(64, 128, 3, 1, 48, seed=12)
+    pf = _pf(golden_weights)
+    bn0 = pf.flow_mlp[0][0].bn
+    rm0 = bn0.running_mean.clone()
+    res, prob, stg, d_gpu, p_gpu = _run_iteration(pf, cpu, cpu["coarse_depth"], 0.25, 0.75, 1, golden_params)
+    assert int(bn0.num_batches_tracked) == int(golden_weights["flow_mlp.0.0.bn.num_batches_tracked"]) + 4
+    assert not torch.equal(bn0.running_mean, rm0)
+    # replay the oracle's 4 sub-cloud MLP inputs through nn.BatchNorm1d
+    dbg = pf.debug_stages()
+    ref = torch.nn.BatchNorm1d(64)
+    ref.running_mean.copy_(golden_weights["flow_mlp.0.0.bn.running_mean"])
+    ref.running_var.copy_(golden_weights["flow_mlp.0.0.bn.running_var"])
+    ref.train()
+    edge = dbg["edge"].cpu()  # [S,B,N,224]
+    for s_ in range(4):
+        ref(O.conv1x1(edge[s_].permute(0, 2, 1).contiguous(), golden_params["mlp0_w"]))
+    assert torch.allclose(bn0.running_mean.cpu(), ref.running_mean, atol=1e-5, rtol=1e-4)
+    assert torch.allclose(bn0.running_var.cpu(), ref.running_var, atol=1e-5, rtol=1e-4)
+    # graph replay == eager
+    gpu = {k: ([t.to(DEV) for t in v] if isinstance(v, list) else (v.to(DEV) if torch.is_tensor(v) else v))
+           for k, v in cpu.items()}
+    with torch.no_grad():
+        eager = PointFlowPass(pf).run(gpu["pyramids"], gpu["coarse_depth"], gpu["cam_params_list"],
+                                      gpu["depth_interval"], gpu["mean"], gpu["std"], gpu["img_hw"])
+        eager = [(d.clone(), p.clone()) for d, p in eager]
+        pfp = PointFlowPass(pf).capture(gpu)
+        assert pfp.launches_per_pass > 30
+        for _ in range(2):
+            outs = pfp.replay()
+        torch.cuda.synchronize()
+    for (de, pe), (dg, pg) in zip(eager, outs):
+        assert torch.allclose(de, dg, atol=2e-4) and torch.allclose(pe, pg, atol=2e-5)
+
+
+def test_full_size_c2_properties_and_oracle_it1():
+    """BASELINE config 2 (640x512, 3 src views): iteration 1 against the oracle (about 1 s of
+    CPU), later iterations through size-independent properties."""
+    from pointmvsnet_b200.point_flow import PointFlow, PointFlowPass
+    from pointmvsnet_b200.parallel import state_dict_from_params
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs, make_flow_params
+    from pointmvsnet_b200.utils.torch_utils import get_knn_3d
+    cpu = make_pointflow_inputs(512, 640, 4, 1, 96, seed=0)
+    params = make_flow_params(seed=1)
+    pf = PointFlow().to(DEV)
+    pf.load_state_dict(state_dict_from_params(params, pf.state_dict()))
+    pf.train()
+    res, prob, stg, d_gpu, p_gpu = _run_iteration(pf, cpu, cpu["coarse_depth"], 0.125, 1.0, 0, params)
+    _check_stages(pf, stg, 1)
+    assert torch.allclose(d_gpu, res, atol=5e-4, rtol=0)
+    assert torch.allclose(p_gpu, prob, atol=5e-5, rtol=0)
+    gpu = {k: ([t.to(DEV) for t in v] if isinstance(v, list) else (v.to(DEV) if torch.is_tensor(v) else v))
+           for k, v in cpu.items()}
+    with torch.no_grad():
+        outs = PointFlowPass(pf).run(gpu["pyramids"], gpu["coarse_depth"], gpu["cam_params_list"],
+                                     gpu["depth_interval"], gpu["mean"], gpu["std"], gpu["img_hw"])
+    itv = cpu["depth_interval"].item()
+    prev = gpu["coarse_depth"]
+    for (d, p), s, isc in zip(outs, (0.125, 0.25, 0.5), (1.0, 0.75, 0.15)):
+        h, w = int(512 * s), int(640 * s)
+        assert tuple(d.shape) == (1, 1, h, w) and tuple(p.shape) == (1, 5, h, w)
+        assert torch.isfinite(d).all() and torch.isfinite(p).all()
+        assert torch.allclose(p.sum(dim=1), torch.ones(1, h, w, device=DEV), atol=1e-5)  # softmax
+        up = torch.nn.functional.interpolate(prev, (h, w), mode="nearest") if prev.shape[2] != h else prev
+        assert ((d - up).abs() <= 2 * isc * itv + 1e-3).all()  # expectation stays inside the hypotheses
+        prev = d
+    # kNN properties on the last iteration's 16 sub-clouds (409 600 points): self first,
+    # indices in range, distances ascending
+    dbg = pf.debug_stages()
+    xyz = dbg["xyz"].reshape(16, 3, 5, 64, 80)
+    idx = get_knn_3d(xyz, 5, 16)
+    N = 5 * 64 * 80
+    assert torch.equal(idx[:, :, 0], torch.arange(N, device=DEV).expand(16, N))
+    assert int(idx.min()) >= 0 and int(idx.max()) < N
+    assert torch.equal(idx.int(), dbg["idx"].reshape(16, N, 16))

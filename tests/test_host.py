@@ -1,0 +1,190 @@
+"""CPU-side tests: C-ABI surface, host logic, error behaviour, multi-process sharding (gloo)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from tests.conftest import ROOT, load_golden
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from pointmvsnet_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "pmvs_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(pmvs_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(_lib.lib, name), "libpmvs_b200.so does not export %s" % name
+    assert set(_lib.EXPORTED) == set(declared)
+    assert _lib.lib.pmvs_version() >= 100
+
+
+def test_argument_errors_are_reported_without_touching_the_gpu():
+    from pointmvsnet_b200 import _lib
+    lib = _lib.lib
+    dummy = C.c_void_p(256)
+    # unsupported knn / kernel size -> PMVS_ERR_ARG + message (checked before any launch)
+    assert lib.pmvs_knn3d(dummy, dummy, None, 1, 5, 8, 8, 5, 7, None) == 1
+    assert b"unsupported knn" in lib.pmvs_last_error()
+    assert lib.pmvs_knn3d(dummy, dummy, None, 1, 5, 8, 8, 4, 16, None) == 1
+    assert lib.pmvs_knn3d(dummy, dummy, dummy, 1, 5, 8, 8, 5, 16, None) == 1  # both outputs given
+    assert lib.pmvs_knn3d(dummy, dummy, None, 1, 1, 2, 2, 3, 32, None) == 1  # knn > window
+    with pytest.raises(RuntimeError):
+        _lib.check(lib.pmvs_gather_knn_forward(None, None, None, 1, 1, 1, 1, None))
+    assert lib.pmvs_gather_knn_forward(None, None, None, 1, 2, 0, 4, None) == 0  # empty input is fine
+    s = _lib.FlowShape()
+    s.B, s.V = 1, 99
+    assert lib.pmvs_point_flow_workspace_bytes(C.byref(s)) == 0
+    assert b"V" in lib.pmvs_last_error()
+
+
+def test_workspace_plan_sizes():
+    from pointmvsnet_b200 import _lib
+    from pointmvsnet_b200.point_flow import PointFlow
+    s = PointFlow.make_shape(1, 4, [(256, 320), (128, 160), (64, 80)], (128, 160), (512, 640), 0.5, True)
+    assert (s.flow_h, s.flow_w, s.ratio) == (256, 320, 4)
+    need = _lib.lib.pmvs_point_flow_workspace_bytes(C.byref(s))
+    rows = 16 * 25600
+    assert need >= rows * (136 + 3 + 16 + 128 + 224 + 64 + 64 + 16) * 4
+    assert need < rows * 700 * 4
+    off = (C.c_size_t * 8)()
+    assert _lib.lib.pmvs_point_flow_debug_offsets(C.byref(s), C.byref(off)) == 0
+    assert all(o % 256 == 0 for o in off)
+    # divisibility required by the sub-grid view (model.py:240-243)
+    bad = PointFlow.make_shape(1, 4, [(256, 320), (128, 160), (64, 80)], (64, 80), (514, 640), 0.5, True)
+    assert _lib.lib.pmvs_point_flow_workspace_bytes(C.byref(bad)) == 0
+
+
+def test_ratio_rule_follows_reference():
+    from pointmvsnet_b200.point_flow import _ratio_for
+    assert [_ratio_for(s, True) for s in (0.125, 0.25, 0.5, 1.0)] == [1, 2, 4, 8]
+    assert _ratio_for(0.25, False) == 1  # train branch: one cloud (model.py:271)
+    with pytest.raises(NotImplementedError):  # model.py:268
+        _ratio_for(0.3, True)
+
+
+def test_state_dict_names_match_reference_checkpoint(golden_weights):
+    from pointmvsnet_b200.point_flow import PointFlow
+    pf = PointFlow()
+    own = pf.state_dict()
+    assert set(own.keys()) == set(golden_weights.keys())
+    for k, v in golden_weights.items():
+        assert tuple(own[k].shape) == tuple(v.shape), k
+    pf.load_reference_state_dict({"module." + k: v for k, v in golden_weights.items()})
+    assert torch.equal(pf.flow_mlp[1].weight, golden_weights["flow_mlp.1.weight"])
+    broken = dict(golden_weights)
+    del broken["flow_mlp.0.1.conv.weight"]
+    with pytest.raises(KeyError):
+        PointFlow().load_reference_state_dict(broken)
+    broken = dict(golden_weights)
+    broken["flow_edge_conv.0.conv1.weight"] = torch.zeros(32, 128, 1)
+    with pytest.raises(ValueError):
+        PointFlow().load_reference_state_dict(broken)
+
+
+def test_no_cpu_fallback():
+    from pointmvsnet_b200.utils.feature_fetcher import FeatureFetcher
+    from pointmvsnet_b200.utils.torch_utils import get_knn_3d
+    from pointmvsnet_b200.networks import EdgeConv
+    from pointmvsnet_b200.functions.gather_knn import gather_knn
+    with pytest.raises(RuntimeError):
+        get_knn_3d(torch.zeros(1, 3, 5, 4, 4), 5, 16)
+    with pytest.raises(RuntimeError):
+        FeatureFetcher()(torch.zeros(1, 1, 4, 8, 8), torch.zeros(1, 3, 2), torch.eye(3).view(1, 1, 3, 3), None)
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            EdgeConv(32, 32)(torch.zeros(1, 32, 10), torch.zeros(1, 10, 16, dtype=torch.long))
+    with pytest.raises(RuntimeError):
+        gather_knn(torch.zeros(1, 2, 3), torch.zeros(1, 3, 2, dtype=torch.long))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pointmvsnet_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("oracle-style", ""), f
+
+
+def test_install_as_pointmvsnet_aliases():
+    import pointmvsnet_b200
+    saved = {k: v for k, v in sys.modules.items() if k == "pointmvsnet" or k.startswith("pointmvsnet.")}
+    try:
+        pointmvsnet_b200.install_as_pointmvsnet()
+        from pointmvsnet.utils.torch_utils import get_knn_3d as a  # noqa
+        from pointmvsnet_b200.utils.torch_utils import get_knn_3d as b
+        assert a is b
+        from pointmvsnet.functions import dgcnn_ext  # noqa
+        assert hasattr(dgcnn_ext, "gather_knn_forward") and hasattr(dgcnn_ext, "gather_knn_backward")
+    finally:
+        for k in [k for k in sys.modules if k == "pointmvsnet" or k.startswith("pointmvsnet.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_synthetic_generator_is_deterministic_and_dtu_shaped():
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    a = make_pointflow_inputs(64, 128, 3, 1, 48, seed=3)
+    b = make_pointflow_inputs(64, 128, 3, 1, 48, seed=3)
+    assert all(torch.equal(x, y) for x, y in zip(a["pyramids"], b["pyramids"]))
+    assert [tuple(p.shape) for p in a["pyramids"]] == [(1, 3, 16, 32, 64), (1, 3, 32, 16, 32), (1, 3, 64, 8, 16)]
+    cams = a["cam_params_list"]
+    assert tuple(cams.shape) == (1, 3, 2, 4, 4)
+    R = cams[0, :, 0, :3, :3]
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(3, 3, 3), atol=1e-5)
+    assert abs(cams[0, 0, 1, 3, 1].item() - 2.5 * 4.24) < 1e-5  # config.py:28
+
+
+def test_shard_views_partition():
+    from pointmvsnet_b200.parallel import shard_views
+    for n, w in ((49, 8), (7, 2), (3, 4), (8, 8)):
+        parts = [shard_views(n, r, w) for r in range(w)]
+        assert sum(parts, []) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from pointmvsnet_b200.parallel import shard_views, gather_depth_maps, gather_ragged_depth_maps
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+views = 5
+mine = shard_views(views, rank, world)
+local = torch.stack([torch.full((1, 4, 6), float(v)) for v in mine])  # "depth map" of view v is v everywhere
+full = gather_ragged_depth_maps(local, views)
+assert full.shape == (views, 1, 4, 6)
+assert torch.equal(full[:, 0, 0, 0], torch.arange(views, dtype=torch.float32)), full[:, 0, 0, 0]
+eq = gather_depth_maps(torch.full((1, 1, 4, 6), float(rank)))
+assert [t[0, 0, 0, 0].item() for t in eq] == [float(r) for r in range(world)]
+dist.barrier()
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_depth_map_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0 and "OK" in out, out
+
+
+def test_bench_algorithmic_bytes_match_survey():
+    sys.path.insert(0, ROOT)
+    import bench
+    alg = bench.algorithmic_bytes_per_pass(512, 640, 4)
+    # C2 fetch traffic 51.0 / 93.7 / 264.8 MB per iteration (sum 409.5 MB)
+    assert abs(alg["fused_fetch"][0] / 1e6 - 409.5) < 1.0
+    assert alg["fused_fetch"][1] == 3
+    assert alg["knn3d"][0] == 537600 * 76
