@@ -128,6 +128,9 @@ typedef struct pmvs_flow_weights {
   float* mlp_run_var[3];
   float momentum;           /* 0.1 (nn/conv.py:17, torch default) */
   float eps;                /* 1e-5 */
+  /* optional BatchNorm num_batches_tracked counters (int64, NULL = skip): += S per call */
+  long long* ec_nbt[3];
+  long long* mlp_nbt[3];
 } pmvs_flow_weights;
 
 typedef struct pmvs_flow_shape {
@@ -141,6 +144,8 @@ typedef struct pmvs_flow_shape {
                          0.25/0.5/1.0 (model.py:237), 1 otherwise; S = ratio^2 sub-clouds */
   int is_test;        /* 1: K *= image_scale (model.py:160-161); 0: K *= 4*image_scale
                          (model.py:162-163) */
+  float interval_scale; /* the hypothesis spacing is interval[b] * interval_scale (fp32 product,
+                           model.py:301 inter_scale * depth_interval); use 1 if pre-multiplied */
 } pmvs_flow_shape;
 
 /* bytes of device workspace pmvs_point_flow_iter needs for this shape */

@@ -30,6 +30,7 @@ class FlowWeights(C.Structure):
         ("ec_run_mean", C.c_void_p * 3), ("ec_run_var", C.c_void_p * 3),
         ("mlp_run_mean", C.c_void_p * 3), ("mlp_run_var", C.c_void_p * 3),
         ("momentum", C.c_float), ("eps", C.c_float),
+        ("ec_nbt", C.c_void_p * 3), ("mlp_nbt", C.c_void_p * 3),
     ]
 
 
@@ -37,7 +38,7 @@ class FlowShape(C.Structure):
     _fields_ = [
         ("B", C.c_int), ("V", C.c_int), ("pyr_h", C.c_int * 3), ("pyr_w", C.c_int * 3),
         ("prev_h", C.c_int), ("prev_w", C.c_int), ("flow_h", C.c_int), ("flow_w", C.c_int),
-        ("image_scale", C.c_float), ("ratio", C.c_int), ("is_test", C.c_int),
+        ("image_scale", C.c_float), ("ratio", C.c_int), ("is_test", C.c_int), ("interval_scale", C.c_float),
     ]
 
 

@@ -325,7 +325,7 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
   }
   // model.py:159-163: K rows 0,1 scaled by image_scale (test) or 4*image_scale (train)
   const float kscale = shape->is_test ? shape->image_scale : (float)(4.0 * (double)shape->image_scale);
-  PMVS_TRY(launch_cam_setup(cam_params, interval, mean, stdv, cam, B, shape->V, kscale, st));
+  PMVS_TRY(launch_cam_setup(cam_params, interval, mean, stdv, cam, B, shape->V, kscale, shape->interval_scale, st));
 
   FusedFetchParams f{};
   for (int l = 0; l < 3; ++l) { f.pyr[l] = pyramids_cl[l]; f.hl[l] = shape->pyr_h[l]; f.wl[l] = shape->pyr_w[l]; }
@@ -373,7 +373,7 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
   HeadArgs h{};
   h.h2 = h2; h.stats = stats + p.st_mlp[2]; h.gamma = wts->mlp_gamma[2]; h.beta = wts->mlp_beta[2];
   h.w3 = wts->mlp_w[3]; h.depth_prev = depth_prev; h.interval = interval; h.depth_out = depth_out;
-  h.prob_out = prob_out; h.eps = wts->eps; h.B = B; h.S = S; h.ratio = shape->ratio; h.h = shape->flow_h;
+  h.prob_out = prob_out; h.eps = wts->eps; h.interval_scale = shape->interval_scale; h.B = B; h.S = S; h.ratio = shape->ratio; h.h = shape->flow_h;
   h.w = shape->flow_w; h.hp = shape->prev_h; h.wp = shape->prev_w;
   PMVS_TRY(launch_flow_head(h, st));
 
@@ -395,7 +395,7 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
       RunUpdate& u = rb.u[rb.n++];
       u.stats = sl; u.run_mean = wts->ec_run_mean[l] + (l > 0 ? c : 0); u.run_var = wts->ec_run_var[l] + (l > 0 ? c : 0);
       u.C = c; u.off_sum = 2 * c; u.off_sq = 3 * c; u.gstride = 4 * c; u.count = (double)rows_per_group * PMVS_KNN;
-      u.ncorr = u.count;
+      u.ncorr = u.count; u.nbt = wts->ec_nbt[l];
     }
   }
   const int mcout2[3] = {64, 64, 16};
@@ -404,7 +404,7 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
       RunUpdate& u = rb.u[rb.n++];
       u.stats = stats + p.st_mlp[l]; u.run_mean = wts->mlp_run_mean[l]; u.run_var = wts->mlp_run_var[l];
       u.C = mcout2[l]; u.off_sum = 0; u.off_sq = mcout2[l]; u.gstride = 2 * mcout2[l];
-      u.count = (double)rows_per_group; u.ncorr = u.count;
+      u.count = (double)rows_per_group; u.ncorr = u.count; u.nbt = wts->mlp_nbt[l];
     }
   }
   PMVS_TRY(launch_bn_running_update(rb, st));

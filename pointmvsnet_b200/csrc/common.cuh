@@ -115,7 +115,7 @@ struct FusedFetchParams {
   int B, V, h, w, hp, wp, ratio;
 };
 int launch_cam_setup(const float* cam_params, const float* interval, const float* mean, const float* stdv,
-                     float* blocks, int B, int V, float kscale, cudaStream_t st);
+                     float* blocks, int B, int V, float kscale, float iscale, cudaStream_t st);
 int launch_fused_fetch(const FusedFetchParams& p, cudaStream_t st);
 size_t cam_block_bytes(int B, int V);
 
@@ -129,7 +129,7 @@ struct HeadArgs {
   const float* interval;    // [B]
   float* depth_out;         // [B,1,h,w]
   float* prob_out;          // [B,5,h,w] or NULL
-  float eps;
+  float eps, interval_scale;
   int B, S, ratio, h, w, hp, wp;
 };
 int launch_flow_head(const HeadArgs& a, cudaStream_t st);
@@ -141,6 +141,7 @@ struct RunUpdate {
   int C, off_sum, off_sq, gstride;
   double count;  // values summed per group
   double ncorr;  // element count nn.BatchNorm sees (for the unbiased running_var)
+  long long* nbt;  // num_batches_tracked (+= groups) or NULL
 };
 struct RunUpdateBatch {
   RunUpdate u[9];

@@ -206,9 +206,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
 // cout channels of one point with float4s; a warp handles 32/(cout/4) points at a time.
 // =======================================================================================
 constexpr int E_THREADS = 256;
-constexpr int E_PTS_PER_BLOCK = 256;  // points per CTA (contiguous -> neighbours overlap in L1)
+constexpr int E_PTS_PER_BLOCK = 128;  // points per CTA (contiguous -> neighbours overlap in L1)
 
-template <int COUT, bool APPLY>
+// KT = compile-time neighbour count (16 on the hot path: indices are fetched as 4 x int4 and
+// the 16 gathers are independent loads in flight); KT = 0 is the generic runtime-K path.
+template <int COUT, bool APPLY, int KT>
 __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
   constexpr int LPP = COUT / 4;             // lanes per point
   constexpr int PPW = 32 / LPP;             // points per warp step
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
   const int g = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sub = lane / LPP, cl = (lane % LPP) * 4;
-  const int K = a.K;
+  const int K = KT > 0 ? KT : a.K;
 
   if (APPLY) {
     const double* s = a.stats + (size_t)g * 4 * COUT;
@@ -256,8 +258,7 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
       gm = *reinterpret_cast<const float4*>(&c_g[1][cl]);
       bt = *reinterpret_cast<const float4*>(&c_b[1][cl]);
     }
-    for (int k = 0; k < K; ++k) {
-      const int nb = __ldg(ip + k);
+    auto body = [&](int nb) {
       const float4 e = ldg4(a.le + (cloud_base + nb) * LD + COUT + cl);
       const float dx = __fsub_rn(e.x, loc.x), dy = __fsub_rn(e.y, loc.y);
       const float dz = __fsub_rn(e.z, loc.z), dw = __fsub_rn(e.w, loc.w);
@@ -271,6 +272,19 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
         sn2.x = fmaf(dx, dx, sn2.x); sn2.y = fmaf(dy, dy, sn2.y);
         sn2.z = fmaf(dz, dz, sn2.z); sn2.w = fmaf(dw, dw, sn2.w);
       }
+    };
+    if constexpr (KT > 0) {
+      static_assert(KT % 4 == 0, "KT");
+      int nbs[KT];
+#pragma unroll
+      for (int q = 0; q < KT / 4; ++q) {
+        const int4 t = __ldg(reinterpret_cast<const int4*>(ip) + q);
+        nbs[4 * q] = t.x; nbs[4 * q + 1] = t.y; nbs[4 * q + 2] = t.z; nbs[4 * q + 3] = t.w;
+      }
+#pragma unroll
+      for (int k = 0; k < KT; ++k) body(nbs[k]);
+    } else {
+      for (int k = 0; k < K; ++k) body(__ldg(ip + k));
     }
     if (APPLY) {
       const float kf = (float)K;
@@ -325,15 +339,21 @@ static int launch_edge(const EdgeArgs& a, cudaStream_t st) {
   static const char* const names[2][4] = {{"edge_stats_16", "edge_stats_32", "edge_stats_64", "edge_stats_128"},
                                           {"edge_apply_16", "edge_apply_32", "edge_apply_64", "edge_apply_128"}};
   prof_begin(names[APPLY ? 1 : 0][a.cout == 16 ? 0 : (a.cout == 32 ? 1 : (a.cout == 64 ? 2 : 3))], st);
+#define PMVS_EDGE_CASE(C)                                                        \
+  case C:                                                                        \
+    if (a.K == 16) edge_kernel<C, APPLY, 16><<<grid, E_THREADS, 0, st>>>(a);     \
+    else edge_kernel<C, APPLY, 0><<<grid, E_THREADS, 0, st>>>(a);                \
+    break;
   switch (a.cout) {
-    case 16: edge_kernel<16, APPLY><<<grid, E_THREADS, 0, st>>>(a); break;
-    case 32: edge_kernel<32, APPLY><<<grid, E_THREADS, 0, st>>>(a); break;
-    case 64: edge_kernel<64, APPLY><<<grid, E_THREADS, 0, st>>>(a); break;
-    case 128: edge_kernel<128, APPLY><<<grid, E_THREADS, 0, st>>>(a); break;
+    PMVS_EDGE_CASE(16)
+    PMVS_EDGE_CASE(32)
+    PMVS_EDGE_CASE(64)
+    PMVS_EDGE_CASE(128)
     default:
       set_error("edgeconv: unsupported out_channels=%d (supported: 16, 32, 64, 128)", a.cout);
       return PMVS_ERR_ARG;
   }
+#undef PMVS_EDGE_CASE
   return check_launch(APPLY ? "edge_apply_kernel" : "edge_stats_kernel", st);
 }
 int launch_edge_stats(const EdgeArgs& a, cudaStream_t st) { return launch_edge<false>(a, st); }
@@ -392,7 +412,7 @@ __global__ void __launch_bounds__(256) flow_head_kernel(const HeadArgs a) {
     e[m] = expf(-raw[m] - mx);
     sum += e[m];
   }
-  const float itv = a.interval[b];
+  const float itv = __fmul_rn(a.interval_scale, a.interval[b]);
   float flow = 0.f;
   const size_t plane = (size_t)a.h * a.w;
   const size_t pix = (size_t)Y * a.w + X;
@@ -425,6 +445,7 @@ int launch_flow_head(const HeadArgs& a, cudaStream_t st) {
 // =======================================================================================
 __global__ void bn_running_update_kernel(const RunUpdateBatch rb) {
   const RunUpdate& u = rb.u[blockIdx.x];
+  if (threadIdx.x == 0 && u.nbt != nullptr) *u.nbt += rb.groups;
   for (int c = threadIdx.x; c < u.C; c += blockDim.x) {
     float rm = u.run_mean[c], rv = u.run_var[c];
     for (int g = 0; g < rb.groups; ++g) {

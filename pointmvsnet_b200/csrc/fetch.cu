@@ -48,7 +48,7 @@ __device__ void inv3x3(const double* m, double* o) {
 // R_inv), :159-163 (K rows 0,1 scaled), :169 (inverse of the reference K).
 __global__ void cam_setup_kernel(const float* __restrict__ cam_params, const float* __restrict__ interval,
                                  const float* __restrict__ mean, const float* __restrict__ stdv,
-                                 float* __restrict__ blocks, int B, int V, float kscale) {
+                                 float* __restrict__ blocks, int B, int V, float kscale, float iscale) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float* out = blocks + (size_t)b * cam_block_floats(V);
@@ -83,7 +83,7 @@ __global__ void cam_setup_kernel(const float* __restrict__ cam_params, const flo
     out[CB_MEAN + r] = mean[b * 3 + r];
     out[CB_STD + r] = stdv[b * 3 + r];
   }
-  out[CB_INTERVAL] = interval[b];
+  out[CB_INTERVAL] = __fmul_rn(iscale, interval[b]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -202,18 +202,21 @@ __global__ void __launch_bounds__(256)
 //   l0 * native[p0] + l1 * native[p1]   (ATen upsample_bilinear2d source index rule)
 // and the two sample taps (floor, floor+1) carry the grid_sample weights
 // (ATen grid_sampler_2d, zeros padding: out-of-range taps contribute nothing).
+// Duplicate native indices are folded and the non-zero entries are compacted to the front,
+// so the consumer loops stop at the first zero weight.
 struct Axis {
   int i[4];
   float w[4];
 };
-__device__ __forceinline__ void axis_entries(float coord, int out_size, int in_size, float scale, Axis& a) {
+__device__ __forceinline__ void axis_entries(float coord, int out_size, int in_size, float scale, bool valid,
+                                             Axis& a) {
   const float f = floorf(coord);
   const int r0 = (int)f;
   const float wt[2] = {__fsub_rn(f + 1.f, coord), __fsub_rn(coord, f)};
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const int r = r0 + s;
-    const bool inb = r >= 0 && r < out_size;
+    const bool inb = valid && r >= 0 && r < out_size;
     float src = __fsub_rn(__fmul_rn(scale, (float)r + 0.5f), 0.5f);
     if (src < 0.f) src = 0.f;
     int p0 = (int)src;
@@ -233,13 +236,38 @@ __device__ __forceinline__ void axis_entries(float coord, int out_size, int in_s
   else if (a.i[2] == a.i[1]) { a.w[1] += a.w[2]; a.w[2] = 0.f; }
   if (a.i[3] == a.i[1]) { a.w[1] += a.w[3]; a.w[3] = 0.f; }
   else if (a.i[3] == a.i[0]) { a.w[0] += a.w[3]; a.w[3] = 0.f; }
+  // compaction: bubble zero weights to the back (stable for the non-zero entries)
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+    for (int j = 0; j < 3 - pass; ++j) {
+      const bool sw = a.w[j] == 0.f;
+      const float tw = a.w[j];
+      const int ti = a.i[j];
+      a.w[j] = sw ? a.w[j + 1] : tw;
+      a.i[j] = sw ? a.i[j + 1] : ti;
+      a.w[j + 1] = sw ? tw : a.w[j + 1];
+      a.i[j + 1] = sw ? ti : a.i[j + 1];
+    }
+  }
 }
 
 constexpr int FETCH_WARPS = 8;
+constexpr int FETCH_DESC = 3 * PMVS_MAX_VIEWS;  // (view, level) sampling descriptors per warp
+
+// Sampling descriptor of one (view, level) for the current hypothesis point: element
+// offsets (already multiplied by the channel count / row pitch) and weights per axis.
+struct __align__(16) Desc {
+  int xo[4];
+  float xw[4];
+  int yo[4];
+  float yw[4];
+};
 
 __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const FusedFetchParams p) {
   __shared__ __align__(16) float cam[cam_block_floats(PMVS_MAX_VIEWS)];
   __shared__ __align__(8) unsigned long long bar;
+  __shared__ Desc desc_all[FETCH_WARPS][FETCH_DESC];
 
   const int b = blockIdx.y;
   const int V = p.V;
@@ -276,20 +304,20 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pix = blockIdx.x * FETCH_WARPS + warp;
   const int h = p.h, w = p.w;
-  if (pix >= h * w) return;
+  if (pix >= h * w) return;  // warp-uniform
   const int Y = pix / w, X = pix - Y * w;
+  Desc* desc = desc_all[warp];
 
-  // lane role: which pyramid level / channel quad this lane owns
-  int lvl, cq;  // level, float4 index inside the level
+  // lane role in the tap phase: which pyramid level / channel quad this lane owns
+  int lvl, cq;
   if (lane < 16) { lvl = 2; cq = lane; }
   else if (lane < 24) { lvl = 1; cq = lane - 16; }
   else if (lane < 28) { lvl = 0; cq = lane - 24; }
   else { lvl = -1; cq = lane - 28; }
   const int C = lvl == 2 ? 64 : (lvl == 1 ? 32 : 16);
   const int ch_off = lvl == 2 ? 48 : (lvl == 1 ? 16 : 0);
-  const int hl = lvl >= 0 ? p.hl[lvl] : 1, wl = lvl >= 0 ? p.wl[lvl] : 1;
-  const float sx = (float)wl / (float)w, sy = (float)hl / (float)h;  // ATen area_pixel_compute_scale
-  const float* lbase = lvl >= 0 ? p.pyr[lvl] + cq * 4 : nullptr;
+  const int lhw = lvl >= 0 ? p.hl[lvl] * p.wl[lvl] : 0;
+  const float* lbase = lvl >= 0 ? p.pyr[lvl] + cq * 4 + (size_t)b * V * lhw * C : nullptr;
 
   // nearest upsample of the previous depth (model.py:153-158; ATen nearest index rule)
   const float nsy = (float)p.hp / (float)h, nsx = (float)p.wp / (float)w;
@@ -311,7 +339,8 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   const int yy = Y / r, ii = Y - yy * r, xx = X / r, jj = X - xx * r;
   const int cloud = (ii * r + jj) * p.B + b;
   const int Npts = PMVS_NUM_HYP * hs * wsub;
-  const float invV = (float)V;
+  const float fV = (float)V;
+  const int ndesc = 3 * V;
 
 #pragma unroll 1
   for (int m = 0; m < PMVS_NUM_HYP; ++m) {
@@ -323,42 +352,60 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
     const float wy = dot3(cam + CB_R0INV + 3, cx, cy, cz);
     const float wz = dot3(cam + CB_R0INV + 6, cx, cy, cz);
 
-    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-#pragma unroll 1
-    for (int v = 0; v < V; ++v) {
+    // ---- phase 1: lanes build the (view, level) sampling descriptors in parallel ----------
+    __syncwarp();
+    for (int d = lane; d < ndesc; d += 32) {
+      const int v = d / 3, l = d - v * 3;
       const float* cv = cam + CB_VIEW + v * CB_VSTRIDE;
       float u, vv;
       project(cv, cv + 9, cv + 12, wx, wy, wz, u, vv);
       const float ix = grid_coord(u, w), iy = grid_coord(vv, h);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lvl >= 0 && usable(ix) && usable(iy)) {
-        Axis ax, ay;
-        axis_entries(ix, w, wl, sx, ax);
-        axis_entries(iy, h, hl, sy, ay);
-        const float* vb = lbase + (size_t)(b * V + v) * hl * wl * C;
+      const bool ok = usable(ix) && usable(iy);
+      const int hl = p.hl[l], wl = p.wl[l];
+      const int Cl = 16 << l;
+      Axis ax, ay;
+      axis_entries(ok ? ix : 0.f, w, wl, (float)wl / (float)w, ok, ax);  // ATen area_pixel_compute_scale
+      axis_entries(ok ? iy : 0.f, h, hl, (float)hl / (float)h, ok, ay);
+      Desc dd;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dd.xo[j] = ax.i[j] * Cl;
+        dd.xw[j] = ax.w[j];
+        dd.yo[j] = ay.i[j] * wl * Cl + v * hl * wl * Cl;
+        dd.yw[j] = ay.w[j];
+      }
+      desc[d] = dd;
+    }
+    __syncwarp();
+
+    // ---- phase 2: lanes span channels; taps of one view at a time ---------------------------
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    if (lvl >= 0) {
+#pragma unroll 1
+      for (int v = 0; v < V; ++v) {
+        const Desc dd = desc[v * 3 + lvl];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int ey = 0; ey < 4; ++ey) {
-          if (ay.w[ey] != 0.f) {
-            const float* row = vb + (size_t)ay.i[ey] * wl * C;
+          if (dd.yw[ey] == 0.f) break;
+          const float* row = lbase + dd.yo[ey];
 #pragma unroll
-            for (int ex = 0; ex < 4; ++ex) {
-              if (ax.w[ex] != 0.f) {
-                const float wgt = __fmul_rn(ay.w[ey], ax.w[ex]);
-                const float4 t = ldg4(row + (size_t)ax.i[ex] * C);
-                acc.x = fmaf(wgt, t.x, acc.x);
-                acc.y = fmaf(wgt, t.y, acc.y);
-                acc.z = fmaf(wgt, t.z, acc.z);
-                acc.w = fmaf(wgt, t.w, acc.w);
-              }
-            }
+          for (int ex = 0; ex < 4; ++ex) {
+            if (dd.xw[ex] == 0.f) break;
+            const float wgt = __fmul_rn(dd.yw[ey], dd.xw[ex]);
+            const float4 t = ldg4(row + dd.xo[ex]);
+            acc.x = fmaf(wgt, t.x, acc.x);
+            acc.y = fmaf(wgt, t.y, acc.y);
+            acc.z = fmaf(wgt, t.z, acc.z);
+            acc.w = fmaf(wgt, t.w, acc.w);
           }
         }
+        // model.py:188-189: mean over views of x and of x**2 (sum in view order)
+        s1.x = __fadd_rn(s1.x, acc.x); s1.y = __fadd_rn(s1.y, acc.y);
+        s1.z = __fadd_rn(s1.z, acc.z); s1.w = __fadd_rn(s1.w, acc.w);
+        s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
+        s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
       }
-      // model.py:188-189: mean over views of x and of x**2 (sum in view order)
-      s1.x = __fadd_rn(s1.x, acc.x); s1.y = __fadd_rn(s1.y, acc.y);
-      s1.z = __fadd_rn(s1.z, acc.z); s1.w = __fadd_rn(s1.w, acc.w);
-      s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
-      s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
     }
 
     const int n = (m * hs + yy) * wsub + xx;
@@ -366,10 +413,10 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
     if (lvl >= 0) {
       float4 o;  // model.py:190: E[x^2] - E[x]^2, unfused
       float a;
-      a = __fdiv_rn(s1.x, invV); o.x = __fsub_rn(__fdiv_rn(s2.x, invV), __fmul_rn(a, a));
-      a = __fdiv_rn(s1.y, invV); o.y = __fsub_rn(__fdiv_rn(s2.y, invV), __fmul_rn(a, a));
-      a = __fdiv_rn(s1.z, invV); o.z = __fsub_rn(__fdiv_rn(s2.z, invV), __fmul_rn(a, a));
-      a = __fdiv_rn(s1.w, invV); o.w = __fsub_rn(__fdiv_rn(s2.w, invV), __fmul_rn(a, a));
+      a = __fdiv_rn(s1.x, fV); o.x = __fsub_rn(__fdiv_rn(s2.x, fV), __fmul_rn(a, a));
+      a = __fdiv_rn(s1.y, fV); o.y = __fsub_rn(__fdiv_rn(s2.y, fV), __fmul_rn(a, a));
+      a = __fdiv_rn(s1.z, fV); o.z = __fsub_rn(__fdiv_rn(s2.z, fV), __fmul_rn(a, a));
+      a = __fdiv_rn(s1.w, fV); o.w = __fsub_rn(__fdiv_rn(s2.w, fV), __fmul_rn(a, a));
       st4(frow + ch_off + cq * 4, o);
     }
     // normalised xyz (model.py:46-48,193): tiled 8x into channels 112..135 and kept planar
@@ -395,9 +442,9 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
 }
 
 int launch_cam_setup(const float* cam_params, const float* interval, const float* mean, const float* stdv,
-                     float* blocks, int B, int V, float kscale, cudaStream_t st) {
+                     float* blocks, int B, int V, float kscale, float iscale, cudaStream_t st) {
   prof_begin("cam_setup", st);
-  cam_setup_kernel<<<cdiv(B, 32), 32, 0, st>>>(cam_params, interval, mean, stdv, blocks, B, V, kscale);
+  cam_setup_kernel<<<cdiv(B, 32), 32, 0, st>>>(cam_params, interval, mean, stdv, blocks, B, V, kscale, iscale);
   return check_launch("cam_setup_kernel", st);
 }
 

@@ -12,7 +12,7 @@
 
 namespace pmvs {
 
-constexpr int KNN_TX = 32, KNN_TY = 4, KNN_TD = 5;
+constexpr int KNN_TX = 32, KNN_TY = 2, KNN_TD = 5;  // 320 threads: 3 CTAs/SM at 62 registers
 
 template <int K>
 __device__ __forceinline__ void knn_insert(float (&bd)[K], int (&bi)[K], float d, int j) {

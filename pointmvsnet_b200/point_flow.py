@@ -142,7 +142,7 @@ class PointFlow(nn.Module):
 
     # ------------------------------------------------------------------ shape / workspace
     @staticmethod
-    def make_shape(B, V, pyr_hw, prev_hw, img_hw, image_scale, is_test):
+    def make_shape(B, V, pyr_hw, prev_hw, img_hw, image_scale, is_test, interval_scale=1.0):
         s = FlowShape()
         s.B, s.V = B, V
         for l in range(3):
@@ -152,6 +152,7 @@ class PointFlow(nn.Module):
         s.image_scale = float(image_scale)
         s.ratio = _ratio_for(image_scale, is_test)
         s.is_test = 1 if is_test else 0
+        s.interval_scale = float(interval_scale)
         return s
 
     def _workspace(self, shape, device):
@@ -164,13 +165,15 @@ class PointFlow(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, estimated_depth_map, interval, image_scale, it=0, *, feature_pyramids, cam_params_list,
-                mean, std, is_test=True, img_hw=None, pyramids_channels_last=None, out=None):
+                mean, std, is_test=True, img_hw=None, pyramids_channels_last=None, out=None, interval_scale=1.0):
         """One refinement iteration (model.py:150-295).
 
         estimated_depth_map [B,1,hp,wp]; interval [B] (= inter_scale * depth_interval,
         model.py:301); feature_pyramids: dict conv1/conv2/conv3 -> [B,V,C,h,w] (or the
         list returned by ``pyramids_to_channels_last`` via ``pyramids_channels_last``);
-        cam_params_list [B,V,2,4,4]; mean/std [B,3].  Returns (flow_result [B,1,h,w],
+        cam_params_list [B,V,2,4,4]; mean/std [B,3].  ``interval_scale`` multiplies
+        ``interval`` inside the kernels (lets the loop pass depth_interval and inter_scale
+        without a separate elementwise launch).  Returns (flow_result [B,1,h,w],
         flow_prob [B,5,h,w])."""
         require_cuda(estimated_depth_map, interval, cam_params_list, mean, std)
         dev = estimated_depth_map.device
@@ -182,7 +185,7 @@ class PointFlow(nn.Module):
         if img_hw is None:
             img_hw = (pyr_hw[0][0] * 2, pyr_hw[0][1] * 2)  # conv1 is at half resolution (networks.py:84-124)
         depth = _lib.f32c(estimated_depth_map)
-        shape = self.make_shape(B, V, pyr_hw, tuple(depth.shape[2:]), img_hw, image_scale, is_test)
+        shape = self.make_shape(B, V, pyr_hw, tuple(depth.shape[2:]), img_hw, image_scale, is_test, interval_scale)
         ws, need = self._workspace(shape, dev)
         w, _keep = self._weights(dev)
         track = self.update_running_stats and self.training
@@ -192,6 +195,8 @@ class PointFlow(nn.Module):
             w.ec_run_var[l] = ptr(bns[l].running_var) if track else None
             w.mlp_run_mean[l] = ptr(bns[3 + l].running_mean) if track else None
             w.mlp_run_var[l] = ptr(bns[3 + l].running_var) if track else None
+            w.ec_nbt[l] = ptr(bns[l].num_batches_tracked) if track else None
+            w.mlp_nbt[l] = ptr(bns[3 + l].num_batches_tracked) if track else None
         h, wd = shape.flow_h, shape.flow_w
         if out is None:
             depth_out = torch.empty(B, 1, h, wd, device=dev, dtype=torch.float32)
@@ -206,9 +211,6 @@ class PointFlow(nn.Module):
             check(lib.pmvs_point_flow_iter(C.byref(shape), C.byref(w), C.byref(pyr_ptrs), ptr(depth), ptr(cams),
                                            ptr(itv), ptr(mean_c), ptr(std_c), ptr(depth_out), ptr(prob_out),
                                            ptr(ws), need, stream_ptr()))
-            if track:
-                for bn in bns:
-                    bn.num_batches_tracked.add_(shape.ratio * shape.ratio)
         self._last = (shape, ws)
         return depth_out, prob_out
 
@@ -249,13 +251,12 @@ class PointFlowPass(object):
         self.static = None
 
     def run(self, pyramids, coarse_depth, cam_params_list, depth_interval, mean, std, img_hw, cl_buffers=None,
-            outs=None, intervals=None):
+            outs=None):
         pyr_cl = PointFlow.pyramids_to_channels_last(pyramids, out=cl_buffers)
         depth = coarse_depth
         results = []
         for i, (s, isc) in enumerate(zip(self.img_scales, self.inter_scales)):
-            itv = intervals[i] if intervals is not None else depth_interval * isc
-            depth, prob = self.pf(depth, itv, s, i, feature_pyramids=None, cam_params_list=cam_params_list, mean=mean,
+            depth, prob = self.pf(depth, depth_interval, s, i, interval_scale=isc, feature_pyramids=None, cam_params_list=cam_params_list, mean=mean,
                                   std=std, is_test=self.is_test, img_hw=img_hw, pyramids_channels_last=pyr_cl,
                                   out=None if outs is None else outs[i])
             results.append((depth, prob))
@@ -280,13 +281,10 @@ class PointFlowPass(object):
         for s in self.img_scales:
             h, w = int(img_hw[0] * s), int(img_hw[1] * s)
             outs.append((torch.empty(B, 1, h, w, device=dev), torch.empty(B, 5, h, w, device=dev)))
-        intervals = [torch.empty_like(st["depth_interval"]) for _ in self.inter_scales]
 
         def body():
-            for i, isc in enumerate(self.inter_scales):
-                torch.mul(st["depth_interval"], isc, out=intervals[i])
             return self.run(st["pyramids"], st["coarse_depth"], st["cam_params_list"], st["depth_interval"],
-                            st["mean"], st["std"], img_hw, cl_buffers=cl, outs=outs, intervals=intervals)
+                            st["mean"], st["std"], img_hw, cl_buffers=cl, outs=outs)
 
         # warm-up on a side stream (allocates the workspace, fills the weight cache)
         side = torch.cuda.Stream(device=dev)

@@ -372,3 +372,26 @@ def test_full_size_c2_properties_and_oracle_it1():
     assert torch.equal(idx[:, :, 0], torch.arange(N, device=DEV).expand(16, N))
     assert int(idx.min()) >= 0 and int(idx.max()) < N
     assert torch.equal(idx.int(), dbg["idx"].reshape(16, N, 16))
+
+
+def test_chained_pass_vs_oracle_pass(golden_weights, golden_params):
+    """The whole 3-iteration loop (model.py:297-303) through PointFlowPass (in-kernel
+    inter_scale multiply) against the oracle's loop.  Errors chain through nearest upsampling,
+    re-projection and kNN near-ties, so the bound is statistical:
+    mean <= 1e-4 * interval and 99.9th percentile <= 1e-3 * interval at every iteration."""
+    from pointmvsnet_b200.point_flow import PointFlowPass
+    gp = load_golden("pass_small.npz")
+    H, W = [int(v) for v in gp["img_hw"]]
+    interval = gp["cams"][:, 0, 1, 3, 1]
+    pyr = [gp["conv1"], gp["conv2"], gp["conv3"]]
+    want = O.point_flow_pass(gp["coarse_depth"], interval, pyr, gp["cams"], gp["mean"], gp["std"], (H, W),
+                             golden_params)
+    pf = _pf(golden_weights)
+    with torch.no_grad():
+        got = PointFlowPass(pf).run([p.to(DEV) for p in pyr], gp["coarse_depth"].to(DEV), gp["cams"].to(DEV),
+                                    interval.to(DEV), gp["mean"].to(DEV), gp["std"].to(DEV), (H, W))
+    for i, ((dw, pw), (dg, pg), isc) in enumerate(zip(want, got, (1.0, 0.75, 0.15))):
+        err = (dg.cpu() - dw).abs().flatten()
+        itv = float(interval[0]) * isc
+        assert err.mean() <= 1e-4 * itv, (i, err.mean(), itv)
+        assert torch.quantile(err, 0.999) <= 1e-3 * itv, (i, torch.quantile(err, 0.999), itv)
