@@ -47,6 +47,12 @@ const char* pmvs_last_error(void);
 /* number of kernels this library has launched since load (all threads, all devices) */
 unsigned long long pmvs_launch_count(void);
 
+/* Arithmetic of the per-point contractions (1x1 convolutions): 3 = tcgen05 kind::tf32 with
+ * error-compensated 3xTF32 (default, fp32-level accuracy), 1 = plain TF32 tensor cores,
+ * 0 = fp32 SIMT FMA kernel.  Process-wide; not thread-safe against concurrent launches. */
+int pmvs_set_gemm_mode(int mode);
+int pmvs_get_gemm_mode(void);
+
 /* Per-launch CUDA-event timing for bench.py's roofline: while enabled every kernel launch of
  * this library is bracketed by two events on its stream (do not enable during graph capture).
  * pmvs_profile_collect synchronises, writes '\n'-separated kernel names and durations (ms)
@@ -108,6 +114,17 @@ int pmvs_edgeconv_pm(const float* x, int ldx, const int32_t* idx32, const float*
                      int bn_train, float* out, int ldo, float* le_scratch, double* stats_scratch,
                      int groups, int rows_per_group, int N, int K, int cin, int cout,
                      pmvs_stream_t stream);
+
+/* ---- a14 building block: 1x1 convolution on points-major rows (nn/conv.py:21-30) ---------- */
+/* y[r, 0:cout] = f(x[r, 0:cin]) * w[cout, cin]^T over groups * rows_per_group rows.
+ * Optional fused input BatchNorm(batch statistics)+ReLU: in_stats [groups, 2*cin] fp64 sums and
+ * sums of squares over in_count values, in_gamma/in_beta [cin].  Optional out_stats
+ * [groups, 2*cout] fp64 (caller zeroes): per-column sum and sum of squares of y are ADDED.
+ * cin % 8 == 0, cin <= 224, cout % 4 == 0, ldx/ldy % 4 == 0. */
+int pmvs_linear_pm(const float* x, int ldx, const float* w, float* y, int ldy, int groups,
+                   int rows_per_group, int cin, int cout, const double* in_stats,
+                   const float* in_gamma, const float* in_beta, double in_count, float eps,
+                   double* out_stats, pmvs_stream_t stream);
 
 /* ---- a1..a15: one PointFlow iteration  (model.py:150-295, test branch :206-269,
  *      train branch :271-293 when is_test == 0) -------------------------------------- */

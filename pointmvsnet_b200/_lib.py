@@ -53,6 +53,8 @@ P, I, LL, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _sig("pmvs_version", I, [])
 _sig("pmvs_last_error", C.c_char_p, [])
 _sig("pmvs_launch_count", C.c_ulonglong, [])
+_sig("pmvs_set_gemm_mode", I, [I])
+_sig("pmvs_get_gemm_mode", I, [])
 _sig("pmvs_profile_enable", I, [I])
 _sig("pmvs_profile_collect", I, [C.c_char_p, C.c_size_t, P, I])
 _sig("pmvs_gather_knn_forward", I, [P, P, P, I, I, I, I, P])
@@ -63,6 +65,7 @@ _sig("pmvs_feature_fetch_backward", I, [P, P, P, P, P, I, I, I, I, I, I, P])
 _sig("pmvs_transpose", I, [P, P, I, I, I, P])
 _sig("pmvs_idx64_to_idx32", I, [P, P, LL, P])
 _sig("pmvs_edgeconv_pm", I, [P, I, P, P, P, P, F, I, I, P, I, P, P, I, I, I, I, I, I, P])
+_sig("pmvs_linear_pm", I, [P, I, P, P, I, I, I, I, I, P, P, P, C.c_double, F, P, P])
 _sig("pmvs_point_flow_workspace_bytes", C.c_size_t, [C.POINTER(FlowShape)])
 _sig("pmvs_point_flow_iter", I, [C.POINTER(FlowShape), C.POINTER(FlowWeights), C.POINTER(C.c_void_p * 3),
                                  P, P, P, P, P, P, P, P, C.c_size_t, P])
@@ -70,9 +73,9 @@ _sig("pmvs_pyramid_to_channels_last", I, [P, P, I, I, I, I, P])
 _sig("pmvs_point_flow_debug_offsets", I, [C.POINTER(FlowShape), C.POINTER(C.c_size_t * 8)])
 
 EXPORTED = [
-    "pmvs_version", "pmvs_last_error", "pmvs_launch_count", "pmvs_profile_enable", "pmvs_profile_collect", "pmvs_gather_knn_forward",
+    "pmvs_version", "pmvs_last_error", "pmvs_launch_count", "pmvs_profile_enable", "pmvs_profile_collect", "pmvs_set_gemm_mode", "pmvs_get_gemm_mode", "pmvs_gather_knn_forward",
     "pmvs_gather_knn_backward", "pmvs_knn3d", "pmvs_feature_fetch", "pmvs_feature_fetch_backward",
-    "pmvs_transpose", "pmvs_idx64_to_idx32", "pmvs_edgeconv_pm", "pmvs_point_flow_workspace_bytes",
+    "pmvs_transpose", "pmvs_idx64_to_idx32", "pmvs_edgeconv_pm", "pmvs_linear_pm", "pmvs_point_flow_workspace_bytes",
     "pmvs_point_flow_iter", "pmvs_pyramid_to_channels_last", "pmvs_point_flow_debug_offsets",
 ]
 
@@ -120,3 +123,8 @@ def profile_collect(max_records=65536):
     n = lib.pmvs_profile_collect(names, len(names), C.cast(ms, C.c_void_p), max_records)
     nm = names.value.decode().split("\n")[:n]
     return [(nm[i], float(ms[i])) for i in range(n)]
+
+
+def set_gemm_mode(mode):
+    """0: fp32 SIMT, 1: TF32 tensor cores, 3: 3xTF32 tensor cores (default)"""
+    check(lib.pmvs_set_gemm_mode(int(mode)))

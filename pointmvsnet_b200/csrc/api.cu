@@ -276,6 +276,20 @@ extern "C" int pmvs_edgeconv_pm(const float* x, int ldx, const int32_t* idx32, c
   return PMVS_OK;
 }
 
+extern "C" int pmvs_linear_pm(const float* x, int ldx, const float* w, float* y, int ldy, int groups,
+                              int rows_per_group, int cin, int cout, const double* in_stats, const float* in_gamma,
+                              const float* in_beta, double in_count, float eps, double* out_stats,
+                              pmvs_stream_t stream) {
+  PMVS_REQUIRE(x && w && y, "linear_pm: NULL pointer");
+  PMVS_REQUIRE(groups > 0 && rows_per_group > 0 && cin > 0 && cout > 0, "linear_pm: bad sizes");
+  PMVS_REQUIRE(in_stats == nullptr || (in_gamma && in_beta && in_count > 0), "linear_pm: incomplete input BN");
+  GemmArgs g{};
+  g.x = x; g.ldx = ldx; g.w = w; g.y = y; g.ldy = ldy; g.groups = groups; g.rows_per_group = rows_per_group;
+  g.cin = cin; g.cout = cout; g.in_stats = in_stats; g.in_gamma = in_gamma; g.in_beta = in_beta;
+  g.in_count = in_count; g.eps = eps; g.out_stats = out_stats;
+  return launch_gemm(g, (cudaStream_t)stream);
+}
+
 extern "C" size_t pmvs_point_flow_workspace_bytes(const pmvs_flow_shape* shape) {
   FlowPlan p;
   if (make_plan(shape, p) != PMVS_OK) return 0;

@@ -89,6 +89,8 @@ struct GemmArgs {
   double* out_stats;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
+// tcgen05 path; returns -1 when it does not apply (shape / alignment / mode) so the caller falls back
+int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, const char* name);
 
 struct EdgeArgs {
   const float* le;  // [R, 2*cout]  (local | edge)

@@ -190,6 +190,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   else if (a.cin == 224 && a.cout == 64) ni = 3;
   else if (a.cin == 64 && a.cout == 64) ni = 4;
   else if (a.cin == 64 && a.cout == 16) ni = 5;
+  {
+    const int rc = launch_gemm_tc(a, st, names[ni]);
+    if (rc >= 0) return rc;
+  }
   prof_begin(names[ni], st);
   if (a.cout <= 16) {
     dim3 grid(tiles, a.groups, cdiv(a.cout, 16));

@@ -253,21 +253,28 @@ __device__ __forceinline__ void axis_entries(float coord, int out_size, int in_s
 }
 
 constexpr int FETCH_WARPS = 8;
-constexpr int FETCH_DESC = 3 * PMVS_MAX_VIEWS;  // (view, level) sampling descriptors per warp
+constexpr int FETCH_TRIPLES_PER_ROUND = 10;  // 30 lanes build 10 (hypothesis, view) triples of level descriptors
 
-// Sampling descriptor of one (view, level) for the current hypothesis point: element
-// offsets (already multiplied by the channel count / row pitch) and weights per axis.
+// Sampling descriptor of one (hypothesis, view, level): element offsets (already multiplied
+// by the channel count / row pitch) and weights per axis, plus the loop bounds shared by the
+// three levels of the same (hypothesis, view) so that the tap loops are warp-uniform.
 struct __align__(16) Desc {
   int xo[4];
   float xw[4];
   int yo[4];
   float yw[4];
+  int nx, ny, pad0, pad1;
 };
+static_assert(sizeof(Desc) == 80, "Desc layout");
+
+__host__ __device__ constexpr size_t fetch_smem_bytes(int V) {
+  return (size_t)FETCH_WARPS * PMVS_NUM_HYP * V * 3 * sizeof(Desc);
+}
 
 __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const FusedFetchParams p) {
   __shared__ __align__(16) float cam[cam_block_floats(PMVS_MAX_VIEWS)];
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ Desc desc_all[FETCH_WARPS][FETCH_DESC];
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
 
   const int b = blockIdx.y;
   const int V = p.V;
@@ -306,18 +313,8 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   const int h = p.h, w = p.w;
   if (pix >= h * w) return;  // warp-uniform
   const int Y = pix / w, X = pix - Y * w;
-  Desc* desc = desc_all[warp];
-
-  // lane role in the tap phase: which pyramid level / channel quad this lane owns
-  int lvl, cq;
-  if (lane < 16) { lvl = 2; cq = lane; }
-  else if (lane < 24) { lvl = 1; cq = lane - 16; }
-  else if (lane < 28) { lvl = 0; cq = lane - 24; }
-  else { lvl = -1; cq = lane - 28; }
-  const int C = lvl == 2 ? 64 : (lvl == 1 ? 32 : 16);
-  const int ch_off = lvl == 2 ? 48 : (lvl == 1 ? 16 : 0);
-  const int lhw = lvl >= 0 ? p.hl[lvl] * p.wl[lvl] : 0;
-  const float* lbase = lvl >= 0 ? p.pyr[lvl] + cq * 4 + (size_t)b * V * lhw * C : nullptr;
+  const int ntriples = PMVS_NUM_HYP * V;
+  Desc* desc = reinterpret_cast<Desc*>(dyn_smem) + (size_t)warp * ntriples * 3;
 
   // nearest upsample of the previous depth (model.py:153-158; ATen nearest index rule)
   const float nsy = (float)p.hp / (float)h, nsx = (float)p.wp / (float)w;
@@ -333,6 +330,71 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   const float uvz = dot3(cam + CB_KINV + 6, px, py, 1.f);
   const float interval = cam[CB_INTERVAL];
 
+  auto world_point = [&](int m, float& wx, float& wy, float& wz) {
+    const float dm = __fadd_rn(dprev, __fmul_rn(interval, (float)(m - 2)));  // model.py:174
+    const float cx = __fsub_rn(__fmul_rn(uvx, dm), cam[CB_T0 + 0]);
+    const float cy = __fsub_rn(__fmul_rn(uvy, dm), cam[CB_T0 + 1]);
+    const float cz = __fsub_rn(__fmul_rn(uvz, dm), cam[CB_T0 + 2]);
+    wx = dot3(cam + CB_R0INV + 0, cx, cy, cz);  // model.py:177
+    wy = dot3(cam + CB_R0INV + 3, cx, cy, cz);
+    wz = dot3(cam + CB_R0INV + 6, cx, cy, cz);
+  };
+
+  // ---- phase 1: 30 lanes build the (hypothesis, view, level) sampling descriptors ----------
+  {
+    const int tl = lane / 3, l = lane - tl * 3;  // triple inside the round, level
+    const int hl = lane < 30 ? p.hl[l] : 1, wl = lane < 30 ? p.wl[l] : 1;
+    const int Cl = 16 << l;
+    const float sxl = (float)wl / (float)w, syl = (float)hl / (float)h;  // ATen area_pixel_compute_scale
+    for (int t0 = 0; t0 < ntriples; t0 += FETCH_TRIPLES_PER_ROUND) {
+      const int t = t0 + tl;
+      const bool act = lane < 30 && t < ntriples;
+      const int m = act ? t / V : 0, v = act ? t - m * V : 0;
+      float wx, wy, wz;
+      world_point(m, wx, wy, wz);
+      const float* cv = cam + CB_VIEW + v * CB_VSTRIDE;
+      float u, vv;
+      project(cv, cv + 9, cv + 12, wx, wy, wz, u, vv);
+      const float ix = grid_coord(u, w), iy = grid_coord(vv, h);
+      const bool ok = act && usable(ix) && usable(iy);
+      Axis ax, ay;
+      axis_entries(ok ? ix : 0.f, w, wl, sxl, ok, ax);
+      axis_entries(ok ? iy : 0.f, h, hl, syl, ok, ay);
+      int nx = (ax.w[0] != 0.f) + (ax.w[1] != 0.f) + (ax.w[2] != 0.f) + (ax.w[3] != 0.f);
+      int ny = (ay.w[0] != 0.f) + (ay.w[1] != 0.f) + (ay.w[2] != 0.f) + (ay.w[3] != 0.f);
+      // loop bounds shared by the three levels of this (hypothesis, view)
+      const int l0 = tl * 3;
+      nx = max(max(__shfl_sync(0xffffffffu, nx, l0 & 31), __shfl_sync(0xffffffffu, nx, (l0 + 1) & 31)),
+               __shfl_sync(0xffffffffu, nx, (l0 + 2) & 31));
+      ny = max(max(__shfl_sync(0xffffffffu, ny, l0 & 31), __shfl_sync(0xffffffffu, ny, (l0 + 1) & 31)),
+               __shfl_sync(0xffffffffu, ny, (l0 + 2) & 31));
+      if (act) {
+        Desc dd;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dd.xo[j] = ax.i[j] * Cl;
+          dd.xw[j] = ax.w[j];
+          dd.yo[j] = (ay.i[j] + v * hl) * wl * Cl;
+          dd.yw[j] = ay.w[j];
+        }
+        dd.nx = nx; dd.ny = ny; dd.pad0 = 0; dd.pad1 = 0;
+        desc[t * 3 + l] = dd;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase 2: lanes span channels (16 x float4 conv3, 8 conv2, 4 conv1) -------------------
+  int lvl, cq;
+  if (lane < 16) { lvl = 2; cq = lane; }
+  else if (lane < 24) { lvl = 1; cq = lane - 16; }
+  else if (lane < 28) { lvl = 0; cq = lane - 24; }
+  else { lvl = -1; cq = lane - 28; }
+  const int lv = lvl >= 0 ? lvl : 0;  // lanes 28..31 shadow level 0 with zero contribution
+  const int C = 16 << lv;
+  const int ch_off = lvl == 2 ? 48 : (lvl == 1 ? 16 : 0);
+  const float* lbase = p.pyr[lv] + (lvl >= 0 ? cq * 4 : 0) + (size_t)b * V * p.hl[lv] * p.wl[lv] * C;
+
   // sub-cloud addressing (model.py:236-255): pixel (y*r+i, x*r+j) -> sub-cloud s=i*r+j
   const int r = p.ratio;
   const int hs = h / r, wsub = w / r;
@@ -340,72 +402,36 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   const int cloud = (ii * r + jj) * p.B + b;
   const int Npts = PMVS_NUM_HYP * hs * wsub;
   const float fV = (float)V;
-  const int ndesc = 3 * V;
 
 #pragma unroll 1
   for (int m = 0; m < PMVS_NUM_HYP; ++m) {
-    const float dm = __fadd_rn(dprev, __fmul_rn(interval, (float)(m - 2)));  // model.py:174
-    const float cx = __fsub_rn(__fmul_rn(uvx, dm), cam[CB_T0 + 0]);
-    const float cy = __fsub_rn(__fmul_rn(uvy, dm), cam[CB_T0 + 1]);
-    const float cz = __fsub_rn(__fmul_rn(uvz, dm), cam[CB_T0 + 2]);
-    const float wx = dot3(cam + CB_R0INV + 0, cx, cy, cz);  // model.py:177
-    const float wy = dot3(cam + CB_R0INV + 3, cx, cy, cz);
-    const float wz = dot3(cam + CB_R0INV + 6, cx, cy, cz);
-
-    // ---- phase 1: lanes build the (view, level) sampling descriptors in parallel ----------
-    __syncwarp();
-    for (int d = lane; d < ndesc; d += 32) {
-      const int v = d / 3, l = d - v * 3;
-      const float* cv = cam + CB_VIEW + v * CB_VSTRIDE;
-      float u, vv;
-      project(cv, cv + 9, cv + 12, wx, wy, wz, u, vv);
-      const float ix = grid_coord(u, w), iy = grid_coord(vv, h);
-      const bool ok = usable(ix) && usable(iy);
-      const int hl = p.hl[l], wl = p.wl[l];
-      const int Cl = 16 << l;
-      Axis ax, ay;
-      axis_entries(ok ? ix : 0.f, w, wl, (float)wl / (float)w, ok, ax);  // ATen area_pixel_compute_scale
-      axis_entries(ok ? iy : 0.f, h, hl, (float)hl / (float)h, ok, ay);
-      Desc dd;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        dd.xo[j] = ax.i[j] * Cl;
-        dd.xw[j] = ax.w[j];
-        dd.yo[j] = ay.i[j] * wl * Cl + v * hl * wl * Cl;
-        dd.yw[j] = ay.w[j];
-      }
-      desc[d] = dd;
-    }
-    __syncwarp();
-
-    // ---- phase 2: lanes span channels; taps of one view at a time ---------------------------
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-    if (lvl >= 0) {
 #pragma unroll 1
-      for (int v = 0; v < V; ++v) {
-        const Desc dd = desc[v * 3 + lvl];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int v = 0; v < V; ++v) {
+      const Desc dd = desc[(m * V + v) * 3 + lv];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int ey = 0; ey < 4; ++ey) {
-          if (dd.yw[ey] == 0.f) break;
+      for (int ey = 0; ey < 4; ++ey) {
+        if (ey < dd.ny) {  // warp-uniform bound
           const float* row = lbase + dd.yo[ey];
 #pragma unroll
           for (int ex = 0; ex < 4; ++ex) {
-            if (dd.xw[ex] == 0.f) break;
-            const float wgt = __fmul_rn(dd.yw[ey], dd.xw[ex]);
-            const float4 t = ldg4(row + dd.xo[ex]);
-            acc.x = fmaf(wgt, t.x, acc.x);
-            acc.y = fmaf(wgt, t.y, acc.y);
-            acc.z = fmaf(wgt, t.z, acc.z);
-            acc.w = fmaf(wgt, t.w, acc.w);
+            if (ex < dd.nx) {  // warp-uniform bound
+              const float wgt = __fmul_rn(dd.yw[ey], dd.xw[ex]);
+              const float4 t = ldg4(row + dd.xo[ex]);
+              acc.x = fmaf(wgt, t.x, acc.x);
+              acc.y = fmaf(wgt, t.y, acc.y);
+              acc.z = fmaf(wgt, t.z, acc.z);
+              acc.w = fmaf(wgt, t.w, acc.w);
+            }
           }
         }
-        // model.py:188-189: mean over views of x and of x**2 (sum in view order)
-        s1.x = __fadd_rn(s1.x, acc.x); s1.y = __fadd_rn(s1.y, acc.y);
-        s1.z = __fadd_rn(s1.z, acc.z); s1.w = __fadd_rn(s1.w, acc.w);
-        s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
-        s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
       }
+      // model.py:188-189: mean over views of x and of x**2 (sum in view order)
+      s1.x = __fadd_rn(s1.x, acc.x); s1.y = __fadd_rn(s1.y, acc.y);
+      s1.z = __fadd_rn(s1.z, acc.z); s1.w = __fadd_rn(s1.w, acc.w);
+      s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
+      s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
     }
 
     const int n = (m * hs + yy) * wsub + xx;
@@ -420,13 +446,15 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
       st4(frow + ch_off + cq * 4, o);
     }
     // normalised xyz (model.py:46-48,193): tiled 8x into channels 112..135 and kept planar
-    const float nx = __fdiv_rn(__fsub_rn(wx, cam[CB_MEAN + 0]), cam[CB_STD + 0]);
-    const float ny = __fdiv_rn(__fsub_rn(wy, cam[CB_MEAN + 1]), cam[CB_STD + 1]);
-    const float nz = __fdiv_rn(__fsub_rn(wz, cam[CB_MEAN + 2]), cam[CB_STD + 2]);
     int quad = -1;
     if (lvl < 0) quad = cq;            // lanes 28..31 -> float4 0..3
     else if (lane < 2) quad = 4 + lane;  // lanes 0,1   -> float4 4,5
     if (quad >= 0) {
+      float wx, wy, wz;
+      world_point(m, wx, wy, wz);
+      const float nx = __fdiv_rn(__fsub_rn(wx, cam[CB_MEAN + 0]), cam[CB_STD + 0]);
+      const float ny = __fdiv_rn(__fsub_rn(wy, cam[CB_MEAN + 1]), cam[CB_STD + 1]);
+      const float nz = __fdiv_rn(__fsub_rn(wz, cam[CB_MEAN + 2]), cam[CB_STD + 2]);
       const int ph = quad % 3;  // float4 #q starts at component (4q) % 3 = q % 3
       float4 o;
       o.x = ph == 0 ? nx : (ph == 1 ? ny : nz);
@@ -434,9 +462,9 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
       o.z = ph == 0 ? nz : (ph == 1 ? nx : ny);
       o.w = o.x;
       st4(frow + 112 + quad * 4, o);
-    }
-    if (lvl < 0 && cq < 3) {
-      p.xyz[((size_t)cloud * 3 + cq) * Npts + n] = cq == 0 ? nx : (cq == 1 ? ny : nz);
+      if (lvl < 0 && cq < 3) {
+        p.xyz[((size_t)cloud * 3 + cq) * Npts + n] = cq == 0 ? nx : (cq == 1 ? ny : nz);
+      }
     }
   }
 }
@@ -450,8 +478,19 @@ int launch_cam_setup(const float* cam_params, const float* interval, const float
 
 int launch_fused_fetch(const FusedFetchParams& p, cudaStream_t st) {
   dim3 grid(cdiv((long long)p.h * p.w, FETCH_WARPS), p.B);
+  const size_t smem = fetch_smem_bytes(p.V);
+  static size_t smem_set = 0;  // per-process high-water mark of the opt-in dynamic smem size
+  if (smem > 40 * 1024 && smem > smem_set) {  // static smem (camera block) counts against the 48 KB default
+    if (cudaFuncSetAttribute(fused_fetch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess) {
+      cudaGetLastError();
+      set_error("fused_fetch: cannot reserve %zu bytes of shared memory (V=%d)", smem, p.V);
+      return PMVS_ERR_CUDA;
+    }
+    smem_set = smem;
+  }
   prof_begin("fused_fetch", st);
-  fused_fetch_kernel<<<grid, FETCH_WARPS * 32, 0, st>>>(p);
+  fused_fetch_kernel<<<grid, FETCH_WARPS * 32, smem, st>>>(p);
   return check_launch("fused_fetch_kernel", st);
 }
 

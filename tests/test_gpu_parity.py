@@ -395,3 +395,41 @@ def test_chained_pass_vs_oracle_pass(golden_weights, golden_params):
         itv = float(interval[0]) * isc
         assert err.mean() <= 1e-4 * itv, (i, err.mean(), itv)
         assert torch.quantile(err, 0.999) <= 1e-3 * itv, (i, torch.quantile(err, 0.999), itv)
+
+
+@pytest.mark.parametrize("mode,rtol", [(0, 2e-6), (3, 1e-5), (1, 3e-3)])
+@pytest.mark.parametrize("cin,cout,rows", [(136, 64, 1000), (224, 64, 25600), (64, 128, 300), (64, 16, 4097), (32, 64, 128)])
+def test_linear_pm_modes_vs_fp64(mode, rtol, cin, cout, rows):
+    """The per-point contraction in its three arithmetic modes (fp32 SIMT, 3xTF32 and TF32 on
+    tcgen05) against an fp64 matmul, with fused input BatchNorm+ReLU and output statistics.
+    Error is normalised by |x|.|w| per output element (rtol)."""
+    from pointmvsnet_b200 import _lib
+    gen = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = torch.randn(rows, cin, generator=gen).to(DEV)
+    w = (torch.randn(cout, cin, generator=gen) / cin ** 0.5).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(cin, generator=gen)).to(DEV)
+    beta = (0.1 * torch.randn(cin, generator=gen)).to(DEV)
+    xs = x.double()
+    in_stats = torch.cat([xs.sum(0), (xs * xs).sum(0)]).contiguous()
+    y = torch.empty(rows, cout, device=DEV)
+    out_stats = torch.zeros(2 * cout, device=DEV, dtype=torch.float64)
+    old = _lib.lib.pmvs_get_gemm_mode()
+    try:
+        _lib.set_gemm_mode(mode)
+        _lib.check(_lib.lib.pmvs_linear_pm(x.data_ptr(), cin, w.data_ptr(), y.data_ptr(), cout, 1, rows, cin, cout,
+                                           in_stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(rows), 1e-5,
+                                           out_stats.data_ptr(), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_gemm_mode(old)
+    mean = xs.mean(0)
+    var = xs.var(0, unbiased=False)
+    xn = torch.relu((xs - mean) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double())
+    want = xn @ w.double().t()
+    scale = xn.abs() @ w.double().abs().t()
+    err = ((y.double() - want).abs() / scale.clamp(min=1e-6)).max().item()
+    assert err < rtol, (mode, cin, cout, err)
+    # plain TF32 truncates the operands (biased), so its column sums drift by ~1e-3 relative
+    srt = 5e-3 if mode == 1 else 1e-4
+    assert torch.allclose(out_stats[:cout], want.sum(0), rtol=srt, atol=srt * scale.sum(0).max().item())
+    assert torch.allclose(out_stats[cout:], (want * want).sum(0), rtol=2 * srt + 1e-4)
