@@ -301,14 +301,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const GemmArgs 
     const int etid = tid - 160;        // 0..127
     const int row = q * 32 + lane;
     uint32_t acc_phase[2] = {0, 0};
-    double cs1 = 0.0, cs2 = 0.0;       // column statistics of column `etid` (if < N_OUT)
+    double cs1 = 0.0, cs2 = 0.0;       // column statistics of (column etid % N_OUT, row part etid / N_OUT)
     int cur_group = -1;
     int it = 0;
     auto flush_stats = [&](int g) {
-      if (a.out_stats != nullptr && g >= 0 && etid < N_OUT) {
+      if (a.out_stats != nullptr && g >= 0 && etid / N_OUT < (128 / N_OUT > 0 ? 128 / N_OUT : 1)) {
         double* o = a.out_stats + (size_t)g * 2 * a.cout;
-        atomicAdd(o + etid, cs1);
-        atomicAdd(o + a.cout + etid, cs2);
+        atomicAdd(o + etid % N_OUT, cs1);
+        atomicAdd(o + a.cout + etid % N_OUT, cs2);
       }
       cs1 = 0.0;
       cs2 = 0.0;
@@ -349,15 +349,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const GemmArgs 
         if (r < rows_valid)
           st4(a.y + (grow0 + r) * a.ldy + c4 * 4, *reinterpret_cast<const float4*>(sD + r * S::D_PITCH + c4 * 4));
       }
-      if (a.out_stats != nullptr && etid < N_OUT) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int r = 0; r < rows_valid; ++r) {
-          const float v = sD[r * S::D_PITCH + etid];
-          s1 += v;
-          s2 = fmaf(v, v, s2);
+      if (a.out_stats != nullptr) {
+        // column statistics: thread -> (column, row part); 4 independent accumulators per sum
+        constexpr int PARTS = 128 / N_OUT > 0 ? 128 / N_OUT : 1;
+        constexpr int RPP = BM / PARTS;
+        const int col = etid % N_OUT, part = etid / N_OUT;
+        if (part < PARTS) {
+          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+          const int r0 = part * RPP;
+          const float* colp = sD + col;
+#pragma unroll 4
+          for (int r = 0; r < RPP; r += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int rr = r0 + r + u;
+              const float v = rr < rows_valid ? colp[rr * S::D_PITCH] : 0.f;
+              s1[u] += v;
+              s2[u] = fmaf(v, v, s2[u]);
+            }
+          }
+          cs1 += (double)((s1[0] + s1[1]) + (s1[2] + s1[3]));
+          cs2 += (double)((s2[0] + s2[1]) + (s2[2] + s2[3]));
         }
-        cs1 += (double)s1;
-        cs2 += (double)s2;
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");   // staging buffer free for the next tile
     }

@@ -188,3 +188,34 @@ def test_bench_algorithmic_bytes_match_survey():
     assert abs(alg["fused_fetch"][0] / 1e6 - 409.5) < 1.0
     assert alg["fused_fetch"][1] == 3
     assert alg["knn3d"][0] == 537600 * 76
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pointmvsnet"), reason="reference checkout not present")
+def test_unchanged_reference_model_imports_our_operators():
+    """Drop-in check (build container only): with install_as_pointmvsnet(reference_root) the
+    reference's UNCHANGED pointmvsnet/model.py resolves its hot-path imports (model.py:8-12) to
+    this package, and its PointMVSNet owns our EdgeConv modules with checkpoint-compatible names."""
+    code = r"""
+import sys
+sys.path.insert(0, %r)
+import pointmvsnet_b200
+pointmvsnet_b200.install_as_pointmvsnet("/root/reference")
+import pointmvsnet.model as m
+import pointmvsnet_b200.networks as ours
+from pointmvsnet_b200.utils.feature_fetcher import FeatureFetcher
+from pointmvsnet_b200.utils.torch_utils import get_knn_3d
+assert m.get_knn_3d is get_knn_3d
+assert m.FeatureFetcher is FeatureFetcher
+net = m.PointMVSNet()
+assert isinstance(net.flow_edge_conv[0], ours.EdgeConvNoC) and isinstance(net.flow_edge_conv[2], ours.EdgeConv)
+assert isinstance(net.feature_fetcher, FeatureFetcher)
+import torch
+sd = torch.load("/root/reference/outputs/dtu_wde3/model_pretrained.pth", map_location="cpu", weights_only=False)["model"]
+net.load_state_dict({k[7:]: v for k, v in sd.items()})
+from pointmvsnet_b200.point_flow import PointFlow
+pf = PointFlow(flow_edge_conv=net.flow_edge_conv, flow_mlp=net.flow_mlp)  # shares the modules
+assert pf.flow_mlp[1].weight is net.flow_mlp[1].weight
+print("DROPIN-OK")
+""" % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "DROPIN-OK" in out.stdout, out.stdout + out.stderr
