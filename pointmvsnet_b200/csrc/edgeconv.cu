@@ -255,23 +255,28 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
     const float4 loc = ldg4(a.le + row * LD + cl);
     const int32_t* ip = a.idx + row * K;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 m, is, gm, bt;
+    // apply: ((d - mean) * istd) * gamma + beta with d = e - loc is evaluated as fma(e, A, c0),
+    // A = istd * gamma, c0 = beta - (mean + loc) * A  (one FFMA per gathered value)
+    float4 A4, c0;
     if (APPLY) {
-      m = *reinterpret_cast<const float4*>(&c_mean[1][cl]);
-      is = *reinterpret_cast<const float4*>(&c_istd[1][cl]);
-      gm = *reinterpret_cast<const float4*>(&c_g[1][cl]);
-      bt = *reinterpret_cast<const float4*>(&c_b[1][cl]);
+      const float4 m = *reinterpret_cast<const float4*>(&c_mean[1][cl]);
+      const float4 is = *reinterpret_cast<const float4*>(&c_istd[1][cl]);
+      const float4 gm = *reinterpret_cast<const float4*>(&c_g[1][cl]);
+      const float4 bt = *reinterpret_cast<const float4*>(&c_b[1][cl]);
+      A4 = make_float4(is.x * gm.x, is.y * gm.y, is.z * gm.z, is.w * gm.w);
+      c0 = make_float4(fmaf(-(m.x + loc.x), A4.x, bt.x), fmaf(-(m.y + loc.y), A4.y, bt.y),
+                       fmaf(-(m.z + loc.z), A4.z, bt.z), fmaf(-(m.w + loc.w), A4.w, bt.w));
     }
     auto body = [&](int nb) {
       const float4 e = ldg4(a.le + (cloud_base + nb) * LD + COUT + cl);
-      const float dx = __fsub_rn(e.x, loc.x), dy = __fsub_rn(e.y, loc.y);
-      const float dz = __fsub_rn(e.z, loc.z), dw = __fsub_rn(e.w, loc.w);
       if (APPLY) {
-        o.x += fmaxf(bn_apply(dx, m.x, is.x, gm.x, bt.x), 0.f);
-        o.y += fmaxf(bn_apply(dy, m.y, is.y, gm.y, bt.y), 0.f);
-        o.z += fmaxf(bn_apply(dz, m.z, is.z, gm.z, bt.z), 0.f);
-        o.w += fmaxf(bn_apply(dw, m.w, is.w, gm.w, bt.w), 0.f);
+        o.x += fmaxf(fmaf(e.x, A4.x, c0.x), 0.f);
+        o.y += fmaxf(fmaf(e.y, A4.y, c0.y), 0.f);
+        o.z += fmaxf(fmaf(e.z, A4.z, c0.z), 0.f);
+        o.w += fmaxf(fmaf(e.w, A4.w, c0.w), 0.f);
       } else {
+        const float dx = __fsub_rn(e.x, loc.x), dy = __fsub_rn(e.y, loc.y);
+        const float dz = __fsub_rn(e.z, loc.z), dw = __fsub_rn(e.w, loc.w);
         sn1.x += dx; sn1.y += dy; sn1.z += dz; sn1.w += dw;
         sn2.x = fmaf(dx, dx, sn2.x); sn2.y = fmaf(dy, dy, sn2.y);
         sn2.z = fmaf(dz, dz, sn2.z); sn2.w = fmaf(dw, dw, sn2.w);

@@ -259,16 +259,19 @@ constexpr int FETCH_TRIPLES_PER_ROUND = 10;  // 30 lanes build 10 (hypothesis, v
 // by the channel count / row pitch) and weights per axis, plus the loop bounds shared by the
 // three levels of the same (hypothesis, view) so that the tap loops are warp-uniform.
 struct __align__(16) Desc {
-  int xo[4];
+  unsigned xo[4];   // byte offsets of the native texels along x (index * C * 4)
   float xw[4];
-  int yo[4];
+  unsigned yo[4];   // byte offsets of (view, row)
   float yw[4];
   int nx, ny, pad0, pad1;
 };
 static_assert(sizeof(Desc) == 80, "Desc layout");
 
-__host__ __device__ constexpr size_t fetch_smem_bytes(int V) {
+__host__ __device__ constexpr size_t fetch_smem_bytes(int V) {  // descriptors
   return (size_t)FETCH_WARPS * PMVS_NUM_HYP * V * 3 * sizeof(Desc);
+}
+__host__ __device__ constexpr size_t fetch_smem_total(int V) {  // + 16 floats of xyz per warp
+  return fetch_smem_bytes(V) + FETCH_WARPS * 16 * sizeof(float);
 }
 
 __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const FusedFetchParams p) {
@@ -372,15 +375,24 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
         Desc dd;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          dd.xo[j] = ax.i[j] * Cl;
+          dd.xo[j] = (unsigned)(ax.i[j] * Cl) * 4u;
           dd.xw[j] = ax.w[j];
-          dd.yo[j] = (ay.i[j] + v * hl) * wl * Cl;
+          dd.yo[j] = (unsigned)((ay.i[j] + v * hl) * wl * Cl) * 4u;
           dd.yw[j] = ay.w[j];
         }
         dd.nx = nx; dd.ny = ny; dd.pad0 = 0; dd.pad1 = 0;
         desc[t * 3 + l] = dd;
       }
     }
+  }
+  // normalised xyz of the 5 hypothesis points (model.py:46-48,193): lane m computes point m
+  float* xyzs = reinterpret_cast<float*>(dyn_smem + fetch_smem_bytes(V)) + warp * 16;
+  if (lane < PMVS_NUM_HYP) {
+    float wx, wy, wz;
+    world_point(lane, wx, wy, wz);
+    xyzs[lane * 3 + 0] = __fdiv_rn(__fsub_rn(wx, cam[CB_MEAN + 0]), cam[CB_STD + 0]);
+    xyzs[lane * 3 + 1] = __fdiv_rn(__fsub_rn(wy, cam[CB_MEAN + 1]), cam[CB_STD + 1]);
+    xyzs[lane * 3 + 2] = __fdiv_rn(__fsub_rn(wz, cam[CB_MEAN + 2]), cam[CB_STD + 2]);
   }
   __syncwarp();
 
@@ -393,7 +405,8 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   const int lv = lvl >= 0 ? lvl : 0;  // lanes 28..31 shadow level 0 with zero contribution
   const int C = 16 << lv;
   const int ch_off = lvl == 2 ? 48 : (lvl == 1 ? 16 : 0);
-  const float* lbase = p.pyr[lv] + (lvl >= 0 ? cq * 4 : 0) + (size_t)b * V * p.hl[lv] * p.wl[lv] * C;
+  const char* lbase =
+      reinterpret_cast<const char*>(p.pyr[lv] + (lvl >= 0 ? cq * 4 : 0) + (size_t)b * V * p.hl[lv] * p.wl[lv] * C);
 
   // sub-cloud addressing (model.py:236-255): pixel (y*r+i, x*r+j) -> sub-cloud s=i*r+j
   const int r = p.ratio;
@@ -401,7 +414,7 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   const int yy = Y / r, ii = Y - yy * r, xx = X / r, jj = X - xx * r;
   const int cloud = (ii * r + jj) * p.B + b;
   const int Npts = PMVS_NUM_HYP * hs * wsub;
-  const float fV = (float)V;
+  const float rV = __frcp_rn((float)V);
 
 #pragma unroll 1
   for (int m = 0; m < PMVS_NUM_HYP; ++m) {
@@ -413,12 +426,12 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
 #pragma unroll
       for (int ey = 0; ey < 4; ++ey) {
         if (ey < dd.ny) {  // warp-uniform bound
-          const float* row = lbase + dd.yo[ey];
+          const char* row = lbase + dd.yo[ey];
 #pragma unroll
           for (int ex = 0; ex < 4; ++ex) {
             if (ex < dd.nx) {  // warp-uniform bound
               const float wgt = __fmul_rn(dd.yw[ey], dd.xw[ex]);
-              const float4 t = ldg4(row + dd.xo[ex]);
+              const float4 t = __ldg(reinterpret_cast<const float4*>(row + dd.xo[ex]));
               acc.x = fmaf(wgt, t.x, acc.x);
               acc.y = fmaf(wgt, t.y, acc.y);
               acc.z = fmaf(wgt, t.z, acc.z);
@@ -437,12 +450,15 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
     const int n = (m * hs + yy) * wsub + xx;
     float* frow = p.feature + ((size_t)cloud * Npts + n) * PMVS_FEAT_CH;
     if (lvl >= 0) {
-      float4 o;  // model.py:190: E[x^2] - E[x]^2, unfused
+      // model.py:188-190: mean(x^2) - mean(x)^2, unfused.  The mean is sum * (1/V), which is
+      // what ATen's CUDA mean kernel computes (MeanOps: acc * factor); identical to sum / V for
+      // V a power of two and within 1 ulp otherwise.
+      float4 o;
       float a;
-      a = __fdiv_rn(s1.x, fV); o.x = __fsub_rn(__fdiv_rn(s2.x, fV), __fmul_rn(a, a));
-      a = __fdiv_rn(s1.y, fV); o.y = __fsub_rn(__fdiv_rn(s2.y, fV), __fmul_rn(a, a));
-      a = __fdiv_rn(s1.z, fV); o.z = __fsub_rn(__fdiv_rn(s2.z, fV), __fmul_rn(a, a));
-      a = __fdiv_rn(s1.w, fV); o.w = __fsub_rn(__fdiv_rn(s2.w, fV), __fmul_rn(a, a));
+      a = __fmul_rn(s1.x, rV); o.x = __fsub_rn(__fmul_rn(s2.x, rV), __fmul_rn(a, a));
+      a = __fmul_rn(s1.y, rV); o.y = __fsub_rn(__fmul_rn(s2.y, rV), __fmul_rn(a, a));
+      a = __fmul_rn(s1.z, rV); o.z = __fsub_rn(__fmul_rn(s2.z, rV), __fmul_rn(a, a));
+      a = __fmul_rn(s1.w, rV); o.w = __fsub_rn(__fmul_rn(s2.w, rV), __fmul_rn(a, a));
       st4(frow + ch_off + cq * 4, o);
     }
     // normalised xyz (model.py:46-48,193): tiled 8x into channels 112..135 and kept planar
@@ -450,11 +466,7 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
     if (lvl < 0) quad = cq;            // lanes 28..31 -> float4 0..3
     else if (lane < 2) quad = 4 + lane;  // lanes 0,1   -> float4 4,5
     if (quad >= 0) {
-      float wx, wy, wz;
-      world_point(m, wx, wy, wz);
-      const float nx = __fdiv_rn(__fsub_rn(wx, cam[CB_MEAN + 0]), cam[CB_STD + 0]);
-      const float ny = __fdiv_rn(__fsub_rn(wy, cam[CB_MEAN + 1]), cam[CB_STD + 1]);
-      const float nz = __fdiv_rn(__fsub_rn(wz, cam[CB_MEAN + 2]), cam[CB_STD + 2]);
+      const float nx = xyzs[m * 3 + 0], ny = xyzs[m * 3 + 1], nz = xyzs[m * 3 + 2];
       const int ph = quad % 3;  // float4 #q starts at component (4q) % 3 = q % 3
       float4 o;
       o.x = ph == 0 ? nx : (ph == 1 ? ny : nz);
@@ -478,7 +490,7 @@ int launch_cam_setup(const float* cam_params, const float* interval, const float
 
 int launch_fused_fetch(const FusedFetchParams& p, cudaStream_t st) {
   dim3 grid(cdiv((long long)p.h * p.w, FETCH_WARPS), p.B);
-  const size_t smem = fetch_smem_bytes(p.V);
+  const size_t smem = fetch_smem_total(p.V);
   static size_t smem_set = 0;  // per-process high-water mark of the opt-in dynamic smem size
   if (smem > 40 * 1024 && smem > smem_set) {  // static smem (camera block) counts against the 48 KB default
     if (cudaFuncSetAttribute(fused_fetch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
