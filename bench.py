@@ -278,21 +278,58 @@ def run_ours(args):
     value = world * n_iter / (ms_per_step / 1e3)
 
     # ---- end-to-end: host buffers in, host result out, copies inside the timed region -----
+    # Two captured graphs with their own static input buffers alternate; the H2D copy of step i+1
+    # (pinned host memory, copy stream) overlaps the compute of step i; the D2H read of the final
+    # depth map closes every step.  Every step's H2D and D2H are inside the timed region.
     host_out = torch.empty(final_depth.shape, dtype=torch.float32).pin_memory()
     h2d = sum(p.numel() * 4 for p in host["pyramids"]) + sum(
         host[k].numel() * 4 for k in ("coarse_depth", "cam_params_list", "depth_interval", "mean", "std"))
     d2h = host_out.numel() * 4
+    with torch.no_grad():
+        pf2 = PointFlow(flow_edge_conv=pf.flow_edge_conv, flow_mlp=pf.flow_mlp).to(dev)  # shares the weights
+        pf2.train()
+        pfp2 = PointFlowPass(pf2, IMG_SCALES, INTER_SCALES).capture(gpu_in)
+    pipes = [pfp, pfp2]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        pfp.copy_inputs(host, non_blocking=True)
-        pfp.replay()
+    def e2e_run(nsteps):
+        """returns total device time (ms) from the first H2D to the last D2H"""
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        t0.record(stream)
+        copy_stream.wait_stream(stream)
+        with torch.cuda.stream(copy_stream):
+            pipes[0].copy_inputs(host, non_blocking=True)
+            copied[0].record(copy_stream)
+        for i in range(nsteps):
+            cur, nxt = i % 2, (i + 1) % 2
+            if i + 1 < nsteps:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(consumed[nxt])  # graph i-1 finished reading those buffers
+                    pipes[nxt].copy_inputs(host, non_blocking=True)
+                    copied[nxt].record(copy_stream)
+            stream.wait_event(copied[cur])
+            flush.zero_()  # cold L2 for every step (timed: ~40 us of the step)
+            pipes[cur].replay()
+            consumed[cur].record(stream)
+            out = pipes[cur].outs[-1][0]
+            if world > 1:
+                gather_depth_maps(out, gathered)
+            host_out.copy_(out, non_blocking=True)
+        t1.record(stream)
+        barrier()
+        t = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
         if world > 1:
-            gather_depth_maps(final_depth, gathered)
-        host_out.copy_(final_depth, non_blocking=True)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
 
-    for _ in range(3):
-        e2e_step()
-    e2e_ms = timed(args.steps, e2e_step) / args.steps
+    e2e_run(3)
+    e2e_ms = e2e_run(args.steps) / args.steps
     e2e_value = world * n_iter / (e2e_ms / 1e3)
 
     # ---- per-kernel CUDA-event timing (eager, not captured) for the roofline ---------------
@@ -367,7 +404,11 @@ def run_ours(args):
                        "parallelism": "dp%d over reference views" % world, "bn": "batch statistics (train mode)",
                        "weights": "random init, reference shapes"},
             "e2e": {"value": round(e2e_value, 2), "unit": "iters/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 5)},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 5),
+                    "how": "pinned host -> device copy of every step's inputs on a copy stream, double-buffered "
+                           "against the previous step's compute; final depth map read back every step; "
+                           "one CUDA-event pair around all steps; a 256 MiB L2 flush runs "
+                           "inside every timed step"},
             "gpu_launches": int(launches_per_pass * args.steps),
             "launches_per_step": int(launches_per_pass),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernel_table,
