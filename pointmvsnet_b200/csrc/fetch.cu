@@ -257,7 +257,7 @@ constexpr int FETCH_TRIPLES_PER_ROUND = 10;  // 30 lanes build 10 (hypothesis, v
 
 // Sampling descriptor of one (hypothesis, view, level): element offsets (already multiplied
 // by the channel count / row pitch) and weights per axis, plus the loop bounds shared by the
-// three levels of the same (hypothesis, view) so that the tap loops are warp-uniform.
+// axis tap counts (the tap loops run to the warp-wide maximum of the step).
 struct __align__(16) Desc {
   unsigned xo[4];   // byte offsets of the native texels along x (index * C * 4)
   float xw[4];
@@ -272,6 +272,76 @@ __host__ __device__ constexpr size_t fetch_smem_bytes(int V) {  // descriptors
 }
 __host__ __device__ constexpr size_t fetch_smem_total(int V) {  // + 16 floats of xyz per warp
   return fetch_smem_bytes(V) + FETCH_WARPS * 16 * sizeof(float);
+}
+
+// One pyramid level L (0: conv1 16 ch, 1: conv2 32 ch, 2: conv3 64 ch) for the 5 hypotheses of a
+// pixel; see "phase 2" in fused_fetch_kernel.
+template <int L>
+__device__ __forceinline__ void level_pass(const FusedFetchParams& p, const Desc* desc, int b, int V, int lane,
+                                           float rV, float* frow0, size_t fstep) {
+  constexpr int C = 16 << L;
+  constexpr int G = C / 4;        // lanes per sample
+  constexpr int S = 32 / G;       // views sampled per step
+  constexpr int CH_OFF = L == 2 ? 48 : (L == 1 ? 16 : 0);
+  const int grp = lane / G, cq = lane % G;
+  const char* lbase = reinterpret_cast<const char*>(p.pyr[L] + cq * 4 + (size_t)b * V * p.hl[L] * p.wl[L] * C);
+#pragma unroll 1
+  for (int m = 0; m < PMVS_NUM_HYP; ++m) {
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll 1
+    for (int v0 = 0; v0 < V; v0 += S) {
+      const int v = v0 + grp;
+      const bool active = v < V;
+      Desc dd = desc[(m * V + (active ? v : 0)) * 3 + L];
+      if (!active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dd.xw[j] = 0.f; dd.yw[j] = 0.f; }
+        dd.nx = 0; dd.ny = 0;
+      }
+      const int nxm = __reduce_max_sync(0xffffffffu, dd.nx);
+      const int nym = __reduce_max_sync(0xffffffffu, dd.ny);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ey = 0; ey < 4; ++ey) {
+        if (ey < nym) {  // warp-uniform bound
+          const char* row = lbase + dd.yo[ey];
+#pragma unroll
+          for (int ex = 0; ex < 4; ++ex) {
+            if (ex < nxm) {  // warp-uniform bound
+              const float wgt = __fmul_rn(dd.yw[ey], dd.xw[ex]);
+              const float4 t = __ldg(reinterpret_cast<const float4*>(row + dd.xo[ex]));
+              acc.x = fmaf(wgt, t.x, acc.x);
+              acc.y = fmaf(wgt, t.y, acc.y);
+              acc.z = fmaf(wgt, t.z, acc.z);
+              acc.w = fmaf(wgt, t.w, acc.w);
+            }
+          }
+        }
+      }
+      s1.x += acc.x; s1.y += acc.y; s1.z += acc.z; s1.w += acc.w;
+      s2.x = fmaf(acc.x, acc.x, s2.x); s2.y = fmaf(acc.y, acc.y, s2.y);
+      s2.z = fmaf(acc.z, acc.z, s2.z); s2.w = fmaf(acc.w, acc.w, s2.w);
+    }
+    // sum over the lane groups (= views)
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) {
+      s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
+      s1.z += __shfl_xor_sync(0xffffffffu, s1.z, off); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, off);
+      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+      s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+    }
+    if (grp == 0) {
+      // model.py:188-190: mean(x^2) - mean(x)^2 (difference unfused); mean = sum * (1/V) as ATen's
+      // CUDA mean kernel computes it
+      float4 o;
+      float a;
+      a = __fmul_rn(s1.x, rV); o.x = __fsub_rn(__fmul_rn(s2.x, rV), __fmul_rn(a, a));
+      a = __fmul_rn(s1.y, rV); o.y = __fsub_rn(__fmul_rn(s2.y, rV), __fmul_rn(a, a));
+      a = __fmul_rn(s1.z, rV); o.z = __fsub_rn(__fmul_rn(s2.z, rV), __fmul_rn(a, a));
+      a = __fmul_rn(s1.w, rV); o.w = __fsub_rn(__fmul_rn(s2.w, rV), __fmul_rn(a, a));
+      st4(frow0 + m * fstep + CH_OFF + cq * 4, o);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const FusedFetchParams p) {
@@ -365,12 +435,6 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
       axis_entries(ok ? iy : 0.f, h, hl, syl, ok, ay);
       int nx = (ax.w[0] != 0.f) + (ax.w[1] != 0.f) + (ax.w[2] != 0.f) + (ax.w[3] != 0.f);
       int ny = (ay.w[0] != 0.f) + (ay.w[1] != 0.f) + (ay.w[2] != 0.f) + (ay.w[3] != 0.f);
-      // loop bounds shared by the three levels of this (hypothesis, view)
-      const int l0 = tl * 3;
-      nx = max(max(__shfl_sync(0xffffffffu, nx, l0 & 31), __shfl_sync(0xffffffffu, nx, (l0 + 1) & 31)),
-               __shfl_sync(0xffffffffu, nx, (l0 + 2) & 31));
-      ny = max(max(__shfl_sync(0xffffffffu, ny, l0 & 31), __shfl_sync(0xffffffffu, ny, (l0 + 1) & 31)),
-               __shfl_sync(0xffffffffu, ny, (l0 + 2) & 31));
       if (act) {
         Desc dd;
 #pragma unroll
@@ -396,87 +460,40 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   }
   __syncwarp();
 
-  // ---- phase 2: lanes span channels (16 x float4 conv3, 8 conv2, 4 conv1) -------------------
-  int lvl, cq;
-  if (lane < 16) { lvl = 2; cq = lane; }
-  else if (lane < 24) { lvl = 1; cq = lane - 16; }
-  else if (lane < 28) { lvl = 0; cq = lane - 24; }
-  else { lvl = -1; cq = lane - 28; }
-  const int lv = lvl >= 0 ? lvl : 0;  // lanes 28..31 shadow level 0 with zero contribution
-  const int C = 16 << lv;
-  const int ch_off = lvl == 2 ? 48 : (lvl == 1 ? 16 : 0);
-  const char* lbase =
-      reinterpret_cast<const char*>(p.pyr[lv] + (lvl >= 0 ? cq * 4 : 0) + (size_t)b * V * p.hl[lv] * p.wl[lv] * C);
-
-  // sub-cloud addressing (model.py:236-255): pixel (y*r+i, x*r+j) -> sub-cloud s=i*r+j
+  // ---- phase 2: one pyramid level at a time, all 32 lanes on that level ----------------------
+  // A level with C channels needs C/4 lanes per (hypothesis, view) sample, so 32/(C/4) views of
+  // the same hypothesis are sampled per step (2 on conv3, 4 on conv2, 8 on conv1): tap loops are
+  // uniform across the warp and no lane idles on a shorter level.  The per-view samples are then
+  // summed over the lane groups with shuffles (sum and sum of squares, model.py:188-189).
   const int r = p.ratio;
   const int hs = h / r, wsub = w / r;
   const int yy = Y / r, ii = Y - yy * r, xx = X / r, jj = X - xx * r;
   const int cloud = (ii * r + jj) * p.B + b;
   const int Npts = PMVS_NUM_HYP * hs * wsub;
   const float rV = __frcp_rn((float)V);
+  float* frow0 = p.feature + ((size_t)cloud * Npts + (size_t)yy * wsub + xx) * PMVS_FEAT_CH;  // hypothesis 0
+  const size_t fstep = (size_t)hs * wsub * PMVS_FEAT_CH;                                       // next hypothesis
 
-#pragma unroll 1
+  level_pass<2>(p, desc, b, V, lane, rV, frow0, fstep);
+  level_pass<1>(p, desc, b, V, lane, rV, frow0, fstep);
+  level_pass<0>(p, desc, b, V, lane, rV, frow0, fstep);
+
+  // normalised xyz: tiled 8x into channels 112..135 (model.py:193-197) and kept planar for the kNN
+#pragma unroll
   for (int m = 0; m < PMVS_NUM_HYP; ++m) {
-    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-#pragma unroll 1
-    for (int v = 0; v < V; ++v) {
-      const Desc dd = desc[(m * V + v) * 3 + lv];
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int ey = 0; ey < 4; ++ey) {
-        if (ey < dd.ny) {  // warp-uniform bound
-          const char* row = lbase + dd.yo[ey];
-#pragma unroll
-          for (int ex = 0; ex < 4; ++ex) {
-            if (ex < dd.nx) {  // warp-uniform bound
-              const float wgt = __fmul_rn(dd.yw[ey], dd.xw[ex]);
-              const float4 t = __ldg(reinterpret_cast<const float4*>(row + dd.xo[ex]));
-              acc.x = fmaf(wgt, t.x, acc.x);
-              acc.y = fmaf(wgt, t.y, acc.y);
-              acc.z = fmaf(wgt, t.z, acc.z);
-              acc.w = fmaf(wgt, t.w, acc.w);
-            }
-          }
-        }
-      }
-      // model.py:188-189: mean over views of x and of x**2 (sum in view order)
-      s1.x = __fadd_rn(s1.x, acc.x); s1.y = __fadd_rn(s1.y, acc.y);
-      s1.z = __fadd_rn(s1.z, acc.z); s1.w = __fadd_rn(s1.w, acc.w);
-      s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
-      s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
-    }
-
-    const int n = (m * hs + yy) * wsub + xx;
-    float* frow = p.feature + ((size_t)cloud * Npts + n) * PMVS_FEAT_CH;
-    if (lvl >= 0) {
-      // model.py:188-190: mean(x^2) - mean(x)^2, unfused.  The mean is sum * (1/V), which is
-      // what ATen's CUDA mean kernel computes (MeanOps: acc * factor); identical to sum / V for
-      // V a power of two and within 1 ulp otherwise.
-      float4 o;
-      float a;
-      a = __fmul_rn(s1.x, rV); o.x = __fsub_rn(__fmul_rn(s2.x, rV), __fmul_rn(a, a));
-      a = __fmul_rn(s1.y, rV); o.y = __fsub_rn(__fmul_rn(s2.y, rV), __fmul_rn(a, a));
-      a = __fmul_rn(s1.z, rV); o.z = __fsub_rn(__fmul_rn(s2.z, rV), __fmul_rn(a, a));
-      a = __fmul_rn(s1.w, rV); o.w = __fsub_rn(__fmul_rn(s2.w, rV), __fmul_rn(a, a));
-      st4(frow + ch_off + cq * 4, o);
-    }
-    // normalised xyz (model.py:46-48,193): tiled 8x into channels 112..135 and kept planar
-    int quad = -1;
-    if (lvl < 0) quad = cq;            // lanes 28..31 -> float4 0..3
-    else if (lane < 2) quad = 4 + lane;  // lanes 0,1   -> float4 4,5
-    if (quad >= 0) {
-      const float nx = xyzs[m * 3 + 0], ny = xyzs[m * 3 + 1], nz = xyzs[m * 3 + 2];
-      const int ph = quad % 3;  // float4 #q starts at component (4q) % 3 = q % 3
+    const float nx = xyzs[m * 3 + 0], ny = xyzs[m * 3 + 1], nz = xyzs[m * 3 + 2];
+    if (lane < 6) {
+      const int ph = lane % 3;  // float4 #q starts at component (4q) % 3 = q % 3
       float4 o;
       o.x = ph == 0 ? nx : (ph == 1 ? ny : nz);
       o.y = ph == 0 ? ny : (ph == 1 ? nz : nx);
       o.z = ph == 0 ? nz : (ph == 1 ? nx : ny);
       o.w = o.x;
-      st4(frow + 112 + quad * 4, o);
-      if (lvl < 0 && cq < 3) {
-        p.xyz[((size_t)cloud * 3 + cq) * Npts + n] = cq == 0 ? nx : (cq == 1 ? ny : nz);
-      }
+      st4(frow0 + m * fstep + 112 + lane * 4, o);
+    } else if (lane < 9) {
+      const int comp = lane - 6;
+      const int n = (m * hs + yy) * wsub + xx;
+      p.xyz[((size_t)cloud * 3 + comp) * Npts + n] = comp == 0 ? nx : (comp == 1 ? ny : nz);
     }
   }
 }
