@@ -275,24 +275,29 @@ __host__ __device__ constexpr size_t fetch_smem_total(int V) {  // + 16 floats o
 }
 
 // One pyramid level L (0: conv1 16 ch, 1: conv2 32 ch, 2: conv3 64 ch) for the 5 hypotheses of a
-// pixel; see "phase 2" in fused_fetch_kernel.
+// pixel; see "phase 2" in fused_fetch_kernel.  A level with C channels needs C/4 lanes per sample,
+// so 32/(C/4) HYPOTHESES are sampled side by side (2 on conv3, 4 on conv2, 8 >= 5 on conv1) and the
+// views are walked sequentially: every lane owns its hypothesis' running sum / sum of squares in
+// view order (model.py:188-189) and no cross-lane reduction is needed.  The hypotheses of a pixel
+// project to nearly the same place in a view, so their tap counts agree and the warp-uniform
+// loop bounds are tight.
 template <int L>
 __device__ __forceinline__ void level_pass(const FusedFetchParams& p, const Desc* desc, int b, int V, int lane,
                                            float rV, float* frow0, size_t fstep) {
   constexpr int C = 16 << L;
   constexpr int G = C / 4;        // lanes per sample
-  constexpr int S = 32 / G;       // views sampled per step
+  constexpr int S = 32 / G;       // hypotheses sampled per step
   constexpr int CH_OFF = L == 2 ? 48 : (L == 1 ? 16 : 0);
   const int grp = lane / G, cq = lane % G;
   const char* lbase = reinterpret_cast<const char*>(p.pyr[L] + cq * 4 + (size_t)b * V * p.hl[L] * p.wl[L] * C);
 #pragma unroll 1
-  for (int m = 0; m < PMVS_NUM_HYP; ++m) {
+  for (int m0 = 0; m0 < PMVS_NUM_HYP; m0 += S) {
+    const int m = m0 + grp;
+    const bool active = m < PMVS_NUM_HYP;
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
 #pragma unroll 1
-    for (int v0 = 0; v0 < V; v0 += S) {
-      const int v = v0 + grp;
-      const bool active = v < V;
-      Desc dd = desc[(m * V + (active ? v : 0)) * 3 + L];
+    for (int v = 0; v < V; ++v) {
+      Desc dd = desc[((active ? m : 0) * V + v) * 3 + L];
       if (!active) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { dd.xw[j] = 0.f; dd.yw[j] = 0.f; }
@@ -318,21 +323,15 @@ __device__ __forceinline__ void level_pass(const FusedFetchParams& p, const Desc
           }
         }
       }
-      s1.x += acc.x; s1.y += acc.y; s1.z += acc.z; s1.w += acc.w;
-      s2.x = fmaf(acc.x, acc.x, s2.x); s2.y = fmaf(acc.y, acc.y, s2.y);
-      s2.z = fmaf(acc.z, acc.z, s2.z); s2.w = fmaf(acc.w, acc.w, s2.w);
+      // model.py:188-189: sums over views of x and x**2, in view order
+      s1.x = __fadd_rn(s1.x, acc.x); s1.y = __fadd_rn(s1.y, acc.y);
+      s1.z = __fadd_rn(s1.z, acc.z); s1.w = __fadd_rn(s1.w, acc.w);
+      s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
+      s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
     }
-    // sum over the lane groups (= views)
-#pragma unroll
-    for (int off = G; off < 32; off <<= 1) {
-      s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
-      s1.z += __shfl_xor_sync(0xffffffffu, s1.z, off); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, off);
-      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
-      s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
-    }
-    if (grp == 0) {
-      // model.py:188-190: mean(x^2) - mean(x)^2 (difference unfused); mean = sum * (1/V) as ATen's
-      // CUDA mean kernel computes it
+    if (active) {
+      // model.py:190: mean(x^2) - mean(x)^2 (difference unfused); mean = sum * (1/V) as ATen's
+      // CUDA mean kernel computes it (identical to sum / V for V a power of two)
       float4 o;
       float a;
       a = __fmul_rn(s1.x, rV); o.x = __fsub_rn(__fmul_rn(s2.x, rV), __fmul_rn(a, a));
@@ -461,10 +460,7 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   __syncwarp();
 
   // ---- phase 2: one pyramid level at a time, all 32 lanes on that level ----------------------
-  // A level with C channels needs C/4 lanes per (hypothesis, view) sample, so 32/(C/4) views of
-  // the same hypothesis are sampled per step (2 on conv3, 4 on conv2, 8 on conv1): tap loops are
-  // uniform across the warp and no lane idles on a shorter level.  The per-view samples are then
-  // summed over the lane groups with shuffles (sum and sum of squares, model.py:188-189).
+  // (see level_pass: hypotheses side by side in lane groups, views sequentially)
   const int r = p.ratio;
   const int hs = h / r, wsub = w / r;
   const int yy = Y / r, ii = Y - yy * r, xx = X / r, jj = X - xx * r;
