@@ -3,11 +3,13 @@
 // The reference materialises dist[B,3*k^3,D,H,W] with a one-hot conv3d and runs topk.
 // Here a CTA stages an xyz tile plus a zero-filled halo in shared memory (the conv's zero
 // padding, torch_utils.py:44: an out-of-grid neighbour IS the zero vector), every thread
-// owns one point, scans its k^3 candidates in the reference's candidate order
-// (d*k*k + h*k + w, torch_utils.py:32-38) and keeps a sorted top-K in registers.
-// Scanning in ascending candidate id with a strict '<' gives the canonical tie order
-// (distance, then candidate id).  Distances use the reference's rounding sequence:
-// single-rounded differences, (dx^2 + dy^2) + dz^2 with no FMA contraction.
+// owns one point and keeps a sorted top-K of 64-bit keys (fp32 distance bits << 32 | candidate
+// id, id = d*k*k + h*k + w as in torch_utils.py:32-38) in registers: non-negative floats order
+// like their bit patterns, so an unsigned key comparison IS the canonical order (distance, then
+// candidate id) and the candidates can be scanned centre-out - the near ones first, so that most
+// later candidates fail the single "worse than the current K-th" test and are never inserted.
+// Distances use the reference's rounding sequence: single-rounded differences,
+// (dx^2 + dy^2) + dz^2 with no FMA contraction.
 #include "common.cuh"
 
 namespace pmvs {
@@ -15,21 +17,30 @@ namespace pmvs {
 constexpr int KNN_TX = 32, KNN_TY = 2, KNN_TD = 5;  // 320 threads: 3 CTAs/SM at 62 registers
 
 template <int K>
-__device__ __forceinline__ void knn_insert(float (&bd)[K], int (&bi)[K], float d, int j) {
+__device__ __forceinline__ void knn_insert(unsigned (&kd)[K], unsigned (&ki)[K], unsigned d, unsigned j) {
+  // keys are (kd, ki) pairs compared as one 64-bit unsigned number
+  const unsigned long long key = ((unsigned long long)d << 32) | j;
 #pragma unroll
   for (int p = K - 1; p > 0; --p) {
-    const bool lt_prev = d < bd[p - 1];
-    const bool lt_cur = d < bd[p];
-    const float nd = lt_prev ? bd[p - 1] : (lt_cur ? d : bd[p]);
-    const int ni = lt_prev ? bi[p - 1] : (lt_cur ? j : bi[p]);
-    bd[p] = nd;
-    bi[p] = ni;
+    const unsigned long long prev = ((unsigned long long)kd[p - 1] << 32) | ki[p - 1];
+    const unsigned long long cur = ((unsigned long long)kd[p] << 32) | ki[p];
+    const bool lt_prev = key < prev;
+    const bool lt_cur = key < cur;
+    kd[p] = lt_prev ? kd[p - 1] : (lt_cur ? d : kd[p]);
+    ki[p] = lt_prev ? ki[p - 1] : (lt_cur ? j : ki[p]);
   }
-  if (d < bd[0]) {
-    bd[0] = d;
-    bi[0] = j;
+  const unsigned long long first = ((unsigned long long)kd[0] << 32) | ki[0];
+  if (key < first) {
+    kd[0] = d;
+    ki[0] = j;
   }
 }
+
+// centre-out scan order of the (dh, dw) window offsets and of the depth offsets
+__constant__ signed char c_ring5[25][2] = {{0, 0},  {-1, 0},  {0, -1}, {0, 1},  {1, 0},   {-1, -1}, {-1, 1}, {1, -1}, {1, 1},
+                                           {-2, 0}, {0, -2},  {0, 2},  {2, 0},  {-2, -1}, {-2, 1},  {-1, -2}, {-1, 2}, {1, -2},
+                                           {1, 2},  {2, -1},  {2, 1},  {-2, -2}, {-2, 2}, {2, -2},  {2, 2}};
+__constant__ signed char c_ring3[9][2] = {{0, 0}, {-1, 0}, {0, -1}, {0, 1}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
 
 template <int KS, int K, typename IdxT>
 __global__ void __launch_bounds__(KNN_TX* KNN_TY* KNN_TD)
@@ -71,30 +82,36 @@ __global__ void __launch_bounds__(KNN_TX* KNN_TY* KNN_TD)
   const float cy = tile[1][czs][cys][cxs];
   const float cz = tile[2][czs][cys][cxs];
 
-  float bd[K];
-  int bi[K];
+  unsigned kd[K], ki[K];   // distance bits / candidate id, sorted ascending as 64-bit keys
 #pragma unroll
   for (int p = 0; p < K; ++p) {
-    bd[p] = __int_as_float(0x7f800000);  // +inf
-    bi[p] = 0;
+    kd[p] = 0x7f800000u;  // +inf
+    ki[p] = 0xffffffffu;
   }
 
 #pragma unroll 1
-  for (int dd = 0; dd < KS; ++dd) {
-#pragma unroll 1
-    for (int dh = 0; dh < KS; ++dh) {
-      const int sz = threadIdx.z + dd, sy = threadIdx.y + dh;
+  for (int ring = 0; ring < KS * KS; ++ring) {
+    const int dh = KS == 5 ? c_ring5[ring][0] : c_ring3[ring][0];
+    const int dw = KS == 5 ? c_ring5[ring][1] : c_ring3[ring][1];
+    const int sy = threadIdx.y + HK + dh, sx = threadIdx.x + HK + dw;
 #pragma unroll
-      for (int dw = 0; dw < KS; ++dw) {
-        const int sx = threadIdx.x + dw;
-        const float ex = __fsub_rn(cx, tile[0][sz][sy][sx]);
-        const float ey = __fsub_rn(cy, tile[1][sz][sy][sx]);
-        const float ez = __fsub_rn(cz, tile[2][sz][sy][sx]);
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
-        if (d2 < bd[K - 1]) knn_insert<K>(bd, bi, d2, (dd * KS + dh) * KS + dw);
-      }
+    for (int q = 0; q < KS; ++q) {
+      // depth offsets centre-out: 0, -1, +1, -2, +2
+      const int dd = (q == 0) ? 0 : ((q & 1) ? -((q + 1) >> 1) : (q >> 1));
+      const int sz = threadIdx.z + HK + dd;
+      const float ex = __fsub_rn(cx, tile[0][sz][sy][sx]);
+      const float ey = __fsub_rn(cy, tile[1][sz][sy][sx]);
+      const float ez = __fsub_rn(cz, tile[2][sz][sy][sx]);
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+      const unsigned db = __float_as_uint(d2);
+      const unsigned j = (unsigned)(((dd + HK) * KS + (dh + HK)) * KS + (dw + HK));
+      // worse than the current K-th (distance, then id)?  NaN distances never enter (db > +inf bits)
+      if (db < kd[K - 1] || (db == kd[K - 1] && j < ki[K - 1])) knn_insert<K>(kd, ki, db, j);
     }
   }
+  int bi[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) bi[p] = (int)ki[p];
 
   // candidate id -> linear index with the reference's global clamp (torch_utils.py:51-59)
   const long long n = (long long)z * HW + (long long)y * W + x;
