@@ -433,3 +433,18 @@ def test_linear_pm_modes_vs_fp64(mode, rtol, cin, cout, rows):
     srt = 5e-3 if mode == 1 else 1e-4
     assert torch.allclose(out_stats[:cout], want.sum(0), rtol=srt, atol=srt * scale.sum(0).max().item())
     assert torch.allclose(out_stats[cout:], (want * want).sum(0), rtol=2 * srt + 1e-4)
+
+
+def test_ragged_shapes_six_views_vs_oracle(golden_params, golden_weights):
+    """A C5-like shape in miniature: sub-grid 37 x 50 (odd, not a multiple of any tile), 6 views
+    (the shared-memory opt-in path of the fetch kernel), iterations 1 and 2, all stages vs oracle."""
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    cpu = make_pointflow_inputs(296, 400, 6, 1, 96, seed=21)
+    pf = _pf(golden_weights)
+    depth = cpu["coarse_depth"]
+    for it, (s_, isc) in enumerate(zip((0.125, 0.25), (1.0, 0.75))):
+        res, prob, stg, d_gpu, p_gpu = _run_iteration(pf, cpu, depth, s_, isc, it, golden_params)
+        _check_stages(pf, stg, 1)
+        assert torch.allclose(d_gpu, res, atol=5e-4, rtol=0), (it, (d_gpu - res).abs().max())
+        assert torch.allclose(p_gpu, prob, atol=5e-5, rtol=0)
+        depth = res
