@@ -40,7 +40,7 @@ METRIC = "PointFlow iters/sec"
 
 
 def workload_name(cfg, H, W, V, D):
-    return "%s: DTU-shape %dx%d, %d src views (V=%d), %d depth hyp, %d flow iters, B=1 ref view per GPU" % (
+    return "%s: DTU-shape %dx%d, %d src views (V=%d), %d depth hyp, %d flow iters, B=1 per pass" % (
         cfg, W, H, V - 1, V, D, len(IMG_SCALES))
 
 
@@ -228,26 +228,58 @@ def run_ours(args):
     H, W, V, D = CONFIGS[args.config]
     n_iter = len(IMG_SCALES)
 
-    # every rank owns a different reference view (different seed): weak scaling
-    host = make_pointflow_inputs(H, W, V, 1, D, seed=rank, pin_memory=True)
-    gpu_in = {k: ([t.to(dev) for t in v] if isinstance(v, list) else (v.to(dev) if torch.is_tensor(v) else v))
-              for k, v in host.items()}
+    # Every rank owns G different reference views (different seeds): weak scaling.  The G views of a
+    # rank are independent passes (own inputs, own workspace, own BatchNorm buffers) whose CUDA
+    # graphs are replayed concurrently on G streams - small launches of one view fill the SMs the
+    # other view leaves idle.  G = 1 is the plain "one pass per step".
+    import copy
+    G = max(1, args.views_in_flight)
+    hosts = [make_pointflow_inputs(H, W, V, 1, D, seed=rank * G + g, pin_memory=True) for g in range(G)]
+    to_dev = lambda h: {k: ([t.to(dev) for t in v] if isinstance(v, list) else (v.to(dev) if torch.is_tensor(v) else v))
+                        for k, v in h.items()}
+    gpu_ins = [to_dev(h) for h in hosts]
+    gpu_in = gpu_ins[0]
     pf = PointFlow().to(dev)
     pf.load_state_dict(state_dict_from_params(make_flow_params(seed=1), pf.state_dict()))
     pf.train()  # BN batch statistics, test.py:58
 
-    with torch.no_grad():
-        pfp = PointFlowPass(pf, IMG_SCALES, INTER_SCALES).capture(gpu_in)
-    launches_per_pass = pfp.launches_per_pass
-    final_depth = pfp.outs[-1][0]
-    gathered = [torch.empty_like(final_depth) for _ in range(world)] if world > 1 else None
+    def capture_set():
+        """G captured passes (one per view in flight); views > 0 get their own module copy so that
+        the BatchNorm running-statistics side effect is neither shared nor skipped."""
+        pipes = []
+        with torch.no_grad():
+            for g in range(G):
+                m = PointFlow(flow_edge_conv=copy.deepcopy(pf.flow_edge_conv), flow_mlp=copy.deepcopy(pf.flow_mlp)).to(dev)
+                m.train()
+                pipes.append(PointFlowPass(m, IMG_SCALES, INTER_SCALES).capture(gpu_ins[g]))
+        return pipes
+
+    set_a = capture_set()
+    launches_per_pass = set_a[0].launches_per_pass
+    h_f, w_f = set_a[0].outs[-1][0].shape[-2:]
+    final_depths = torch.empty(G, 1, h_f, w_f, device=dev)   # the step's result: G final depth maps
+    gathered = [torch.empty_like(final_depths) for _ in range(world)] if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
+    side = [torch.cuda.Stream(device=dev) for _ in range(G)]
+
+    def replay_set(pipes):
+        if G == 1:
+            pipes[0].replay()
+            final_depths[0].copy_(pipes[0].outs[-1][0][0])
+            return
+        for g in range(G):
+            side[g].wait_stream(stream)
+            with torch.cuda.stream(side[g]):
+                pipes[g].replay()
+                final_depths[g].copy_(pipes[g].outs[-1][0][0])
+        for g in range(G):
+            stream.wait_stream(side[g])
 
     def step():
-        pfp.replay()
+        replay_set(set_a)
         if world > 1:
-            gather_depth_maps(final_depth, gathered)
+            gather_depth_maps(final_depths, gathered)
 
     def barrier():
         if world > 1:
@@ -273,28 +305,27 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         step()
     clk_p, clk_f = sample_clocks_start(local) if rank == 0 else (None, None)
-    n0 = _lib.launch_count()
     total_ms = timed(args.steps, step)
     clocks = sample_clocks_stop(clk_p, clk_f) if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    value = world * n_iter / (ms_per_step / 1e3)
+    value = world * G * n_iter / (ms_per_step / 1e3)
 
     # ---- end-to-end: host buffers in, host result out, copies inside the timed region -----
-    # Two captured graphs with their own static input buffers alternate; the H2D copy of step i+1
-    # (pinned host memory, copy stream) overlaps the compute of step i; the D2H read of the final
-    # depth map closes every step.  Every step's H2D and D2H are inside the timed region.
-    host_out = torch.empty(final_depth.shape, dtype=torch.float32).pin_memory()
-    h2d = sum(p.numel() * 4 for p in host["pyramids"]) + sum(
-        host[k].numel() * 4 for k in ("coarse_depth", "cam_params_list", "depth_interval", "mean", "std"))
+    # Two sets of captured graphs with their own static input buffers alternate; the H2D copies of
+    # step i+1 (pinned host memory, copy stream) overlap the compute of step i; the D2H read of the
+    # step's final depth maps closes every step.  Every step's H2D and D2H are inside the timed region.
+    host_out = torch.empty(final_depths.shape, dtype=torch.float32).pin_memory()
+    h2d = G * (sum(p.numel() * 4 for p in hosts[0]["pyramids"]) + sum(
+        hosts[0][k].numel() * 4 for k in ("coarse_depth", "cam_params_list", "depth_interval", "mean", "std")))
     d2h = host_out.numel() * 4
-    with torch.no_grad():
-        pf2 = PointFlow(flow_edge_conv=pf.flow_edge_conv, flow_mlp=pf.flow_mlp).to(dev)  # shares the weights
-        pf2.train()
-        pfp2 = PointFlowPass(pf2, IMG_SCALES, INTER_SCALES).capture(gpu_in)
-    pipes = [pfp, pfp2]
+    sets = [set_a, capture_set()]
     copy_stream = torch.cuda.Stream(device=dev)
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def copy_set(pipes):
+        for g in range(G):
+            pipes[g].copy_inputs(hosts[g], non_blocking=True)
 
     def e2e_run(nsteps):
         """returns total device time (ms) from the first H2D to the last D2H"""
@@ -305,24 +336,23 @@ def run_ours(args):
         t0.record(stream)
         copy_stream.wait_stream(stream)
         with torch.cuda.stream(copy_stream):
-            pipes[0].copy_inputs(host, non_blocking=True)
+            copy_set(sets[0])
             copied[0].record(copy_stream)
         for i in range(nsteps):
             cur, nxt = i % 2, (i + 1) % 2
             if i + 1 < nsteps:
                 with torch.cuda.stream(copy_stream):
                     if i >= 1:
-                        copy_stream.wait_event(consumed[nxt])  # graph i-1 finished reading those buffers
-                    pipes[nxt].copy_inputs(host, non_blocking=True)
+                        copy_stream.wait_event(consumed[nxt])  # step i-1 finished reading those buffers
+                    copy_set(sets[nxt])
                     copied[nxt].record(copy_stream)
             stream.wait_event(copied[cur])
             flush.zero_()  # cold L2 for every step (timed: ~40 us of the step)
-            pipes[cur].replay()
+            replay_set(sets[cur])
             consumed[cur].record(stream)
-            out = pipes[cur].outs[-1][0]
             if world > 1:
-                gather_depth_maps(out, gathered)
-            host_out.copy_(out, non_blocking=True)
+                gather_depth_maps(final_depths, gathered)
+            host_out.copy_(final_depths, non_blocking=True)
         t1.record(stream)
         barrier()
         t = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
@@ -332,7 +362,7 @@ def run_ours(args):
 
     e2e_run(3)
     e2e_ms = e2e_run(args.steps) / args.steps
-    e2e_value = world * n_iter / (e2e_ms / 1e3)
+    e2e_value = world * G * n_iter / (e2e_ms / 1e3)
 
     # ---- per-kernel CUDA-event timing (eager, not captured) for the roofline ---------------
     roofline = None
@@ -401,7 +431,10 @@ def run_ours(args):
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.config, H, W, V, D),
-                       "step": "one 3-iteration point_flow pass per GPU, CUDA-graph replay + NCCL all-gather of depth maps",
+                       "step": "%d reference view(s) in flight per GPU: one 3-iteration point_flow pass each (B=1, own "
+                               "BatchNorm statistics), CUDA-graph replays on %d stream(s) + NCCL all-gather of the "
+                               "final depth maps" % (G, G),
+                       "views_in_flight": G,
                        "l2": "flushed between steps (256 MiB memset, untimed); per-step CUDA events, max over ranks",
                        "parallelism": "dp%d over reference views" % world, "bn": "batch statistics (train mode)",
                        "weights": "random init, reference shapes"},
@@ -411,8 +444,8 @@ def run_ours(args):
                            "against the previous step's compute; final depth map read back every step; "
                            "one CUDA-event pair around all steps; a 256 MiB L2 flush runs "
                            "inside every timed step"},
-            "gpu_launches": int(launches_per_pass * args.steps),
-            "launches_per_step": int(launches_per_pass),
+            "gpu_launches": int(launches_per_pass * G * args.steps),
+            "launches_per_step": int(launches_per_pass * G),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernel_table,
         }
         print(json.dumps(line))
@@ -429,6 +462,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--views-in-flight", type=int, default=2,
+                    help="independent reference views whose passes run concurrently on one GPU (default 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
