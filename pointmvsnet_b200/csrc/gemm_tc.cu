@@ -138,7 +138,13 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const GemmArgs a) 
   using S = Smem<N_OUT, NSPLIT>;
   constexpr int NPL = S::NPL;
   constexpr bool SPLIT = NSPLIT == 3;
-  constexpr int TMEM_COLS = N_OUT < 32 ? 32 : N_OUT;  // power of two >= 32
+  // 3xTF32 with N <= 64 stacks [Bhi ; Blo] into one N' = 2N operand: A_hi * [Bhi;Blo] is ONE MMA that
+  // reads A_hi once (accumulator columns [0,N) = Ahi*Bhi, [N,2N) = Ahi*Blo), and A_lo * B_hi
+  // accumulates into [N,2N); the epilogue adds the two halves.  14 KB instead of 18 KB of
+  // shared-memory operand reads per k-step - the resource that bounds this kernel.
+  constexpr bool STACKED = SPLIT && N_OUT <= 64;
+  constexpr int ACC_COLS = STACKED ? 2 * N_OUT : N_OUT;
+  constexpr int TMEM_COLS = ACC_COLS < 32 ? 32 : ACC_COLS;  // power of two >= 32
   constexpr int A_LD = BM * 8 / NUM_THREADS;          // float4 loads per thread per chunk (4)
   constexpr int B_LD = (N_OUT * 8 + NUM_THREADS - 1) / NUM_THREADS;
   extern __shared__ unsigned char smem_raw[];
@@ -245,7 +251,11 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const GemmArgs a) 
       const uint32_t b_hi = smem_u32(sB), b_lo = b_hi + S::B_PLANE_BYTES;
       for (int j = 0; j < ksteps; ++j) {
         const uint32_t acc = (c == 0 && j == 0) ? 0u : 1u;
-        if (SPLIT) {
+        if (STACKED) {
+          // B planes are contiguous in shared memory: rows [0,N) = Bhi, [N,2N) = Blo
+          umma_tf32(tmem_base, make_desc(a_hi + j * 32), make_desc(b_hi + j * 32), make_idesc(BM, 2 * N_OUT), acc);
+          umma_tf32(tmem_base + N_OUT, make_desc(a_lo + j * 32), make_desc(b_hi + j * 32), idesc, 1u);
+        } else if (SPLIT) {
           umma_tf32(tmem_base, make_desc(a_lo + j * 32), make_desc(b_hi + j * 32), idesc, acc);
           umma_tf32(tmem_base, make_desc(a_hi + j * 32), make_desc(b_lo + j * 32), idesc, 1u);
           umma_tf32(tmem_base, make_desc(a_hi + j * 32), make_desc(b_hi + j * 32), idesc, 1u);
@@ -271,6 +281,12 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const GemmArgs a) 
     for (int cb = 0; cb < CPW / CB; ++cb) {
       float v[CB];
       tmem_ld<CB>(taddr + cb * CB, v);
+      if (STACKED) {  // add the small-terms half of the accumulator
+        float v2[CB];
+        tmem_ld<CB>(taddr + N_OUT + cb * CB, v2);
+#pragma unroll
+        for (int j = 0; j < CB; ++j) v[j] += v2[j];
+      }
 #pragma unroll
       for (int j = 0; j < CB; j += 4)
         *reinterpret_cast<float4*>(sD + row * S::D_PITCH + half * CPW + cb * CB + j) =
