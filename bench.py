@@ -222,8 +222,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line only
+        # NCCL writes its version banner / debug lines to stdout; keep stdout to ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "nccl_debug.%h.%p.log"))
         dist.init_process_group("nccl", device_id=dev)
     H, W, V, D = CONFIGS[args.config]
     n_iter = len(IMG_SCALES)
