@@ -90,6 +90,17 @@ int pmvs_feature_fetch_backward(const float* grad_out, const float* pts, const f
                                 const float* extrinsics, float* grad_maps, int B, int V, int C,
                                 int H, int W, int N, pmvs_stream_t stream);
 
+/* ---- (next row) coarse-stage plane sweep: fetch + variance  (model.py:54-113) ------ */
+/* features [B,V,C,h,w] (coarse_img_conv conv3 per view, view 0 = reference), cam_params
+ * [B,V,2,4,4] at full image resolution (K rows 0,1 are divided by 2, and by 8 in total when
+ * is_test, model.py:58-61; depth_start / interval / num_depth are read from cam_params[:,0,1,3,:])
+ * -> cost [B,C,D,h,w]: variance over views of the features fetched at the D depth-hypothesis planes,
+ * the reference view contributing its un-warped feature (model.py:103-113).  C % 16 == 0.
+ * workspace: at least B*(28+24V)*4 bytes. */
+int pmvs_cost_volume(const float* features, const float* cam_params, float* cost, void* workspace,
+                     size_t workspace_bytes, int B, int V, int C, int h, int w, int D, int is_test,
+                     pmvs_stream_t stream);
+
 /* ---- layout helpers used by the module-level API --------------------------------- */
 /* batched 2-D transpose: in [batch, R, C] -> out [batch, C, R] */
 int pmvs_transpose(const float* in, float* out, int batch, int R, int C, pmvs_stream_t stream);

@@ -315,6 +315,40 @@ def build_point_features(depth, interval, image_scale, pyramids, cam_params, mea
 
 
 # --------------------------------------------------------------------------- #
+# (f-1) coarse cost volume: plane-sweep fetch + variance  (model.py:54-113)
+# --------------------------------------------------------------------------- #
+def coarse_cost_volume(feature_list, cam_params, is_test=True):
+    """feature_list [B,V,C,h,w] (coarse_img_conv "conv3" per view, model.py:71-77),
+    cam_params [B,V,2,4,4] -> cost volume [B,C,D,h,w] (model.py:113) and the depth
+    hypotheses [B,D].  The reference view's fetched features are overwritten by the
+    un-warped reference feature (model.py:103-106)."""
+    B, V, C, h, w = feature_list.shape
+    ext = cam_params[:, :, 0, :3, :4]
+    R = ext[:, :, :, :3]
+    t = ext[:, :, :, 3:4]
+    R_inv = torch.inverse(R)
+    K = cam_params[:, :, 1, :3, :3].clone()
+    K[:, :, :2, :3] = K[:, :, :2, :3] / 2.0  # model.py:59
+    if is_test:
+        K[:, :, :2, :3] = K[:, :, :2, :3] / 4.0  # model.py:60-61
+    depth_start = cam_params[:, 0, 1, 3, 0]
+    depth_interval = cam_params[:, 0, 1, 3, 1]
+    D = int(cam_params[0, 0, 1, 3, 2].long())
+    depth_end = depth_start + (D - 1) * depth_interval  # model.py:67
+    depths = torch.stack([torch.linspace(depth_start[i], depth_end[i], D) for i in range(B)], dim=0)  # [B,D]
+    grid = get_pixel_grids(h, w).view(1, 1, 3, -1).expand(B, 1, 3, -1)
+    uv = torch.matmul(torch.inverse(K[:, 0]).unsqueeze(1), grid)  # [B,1,3,hw]
+    cam_pts = (uv.unsqueeze(3) * depths.view(B, 1, 1, D, 1)).view(B, 1, 3, -1)  # model.py:93
+    world = torch.matmul(R_inv[:, 0:1], cam_pts - t[:, 0:1]).transpose(1, 2).contiguous().view(B, 3, -1)
+    pf = feature_fetch(feature_list, world, K, ext)  # model.py:102
+    ref = feature_list[:, 0].unsqueeze(2).expand(-1, -1, D, -1, -1).contiguous().view(B, C, -1)
+    pf[:, 0] = ref  # model.py:103-106
+    avg = pf.mean(dim=1)
+    avg2 = (pf ** 2).mean(dim=1)
+    return (avg2 - avg ** 2).view(B, C, D, h, w), depths
+
+
+# --------------------------------------------------------------------------- #
 # a1: one PointFlow iteration  (model.py:150-295)
 # --------------------------------------------------------------------------- #
 def point_flow(depth, interval, image_scale, pyramids, cam_params, mean, std, img_hw,

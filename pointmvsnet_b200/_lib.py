@@ -62,6 +62,7 @@ _sig("pmvs_gather_knn_backward", I, [P, P, P, I, I, I, I, P])
 _sig("pmvs_knn3d", I, [P, P, P, I, I, I, I, I, I, P])
 _sig("pmvs_feature_fetch", I, [P, P, P, P, P, I, I, I, I, I, I, P])
 _sig("pmvs_feature_fetch_backward", I, [P, P, P, P, P, I, I, I, I, I, I, P])
+_sig("pmvs_cost_volume", I, [P, P, P, P, C.c_size_t, I, I, I, I, I, I, I, P])
 _sig("pmvs_transpose", I, [P, P, I, I, I, P])
 _sig("pmvs_idx64_to_idx32", I, [P, P, LL, P])
 _sig("pmvs_edgeconv_pm", I, [P, I, P, P, P, P, F, I, I, P, I, P, P, I, I, I, I, I, I, P])
@@ -75,7 +76,7 @@ _sig("pmvs_point_flow_debug_offsets", I, [C.POINTER(FlowShape), C.POINTER(C.c_si
 EXPORTED = [
     "pmvs_version", "pmvs_last_error", "pmvs_launch_count", "pmvs_profile_enable", "pmvs_profile_collect", "pmvs_set_gemm_mode", "pmvs_get_gemm_mode", "pmvs_gather_knn_forward",
     "pmvs_gather_knn_backward", "pmvs_knn3d", "pmvs_feature_fetch", "pmvs_feature_fetch_backward",
-    "pmvs_transpose", "pmvs_idx64_to_idx32", "pmvs_edgeconv_pm", "pmvs_linear_pm", "pmvs_point_flow_workspace_bytes",
+    "pmvs_cost_volume", "pmvs_transpose", "pmvs_idx64_to_idx32", "pmvs_edgeconv_pm", "pmvs_linear_pm", "pmvs_point_flow_workspace_bytes",
     "pmvs_point_flow_iter", "pmvs_pyramid_to_channels_last", "pmvs_point_flow_debug_offsets",
 ]
 

@@ -80,10 +80,10 @@ __global__ void cam_setup_kernel(const float* __restrict__ cam_params, const flo
     }
   }
   for (int r = 0; r < 3; ++r) {
-    out[CB_MEAN + r] = mean[b * 3 + r];
-    out[CB_STD + r] = stdv[b * 3 + r];
+    out[CB_MEAN + r] = mean ? mean[b * 3 + r] : 0.f;
+    out[CB_STD + r] = stdv ? stdv[b * 3 + r] : 1.f;
   }
-  out[CB_INTERVAL] = __fmul_rn(iscale, interval[b]);
+  out[CB_INTERVAL] = interval ? __fmul_rn(iscale, interval[b]) : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -494,6 +494,81 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// (3) coarse-stage plane sweep: fetch + variance -> cost volume  (reference model.py:81-113)
+// ---------------------------------------------------------------------------------------
+// One thread per hypothesis point (d, y, x); channels in chunks of 16 so that sum / sum of squares
+// stay in registers; the source-view projection is recomputed per chunk (cheap next to 64 taps).
+// The reference view contributes its un-warped feature (model.py:103-106).  NCHW reads and the
+// [B,C,D,h,w] writes are coalesced across x.
+constexpr int CV_CH = 16;
+__global__ void __launch_bounds__(256)
+    cost_volume_kernel(const float* __restrict__ feat, const float* __restrict__ cam_params,
+                       const float* __restrict__ cam_blocks, float* __restrict__ cost, int V, int C, int h, int w,
+                       int D) {
+  __shared__ float cam[cam_block_floats(PMVS_MAX_VIEWS)];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < cam_block_floats(V); i += blockDim.x)
+    cam[i] = cam_blocks[(size_t)b * cam_block_floats(V) + i];
+  __syncthreads();
+  const int hw = h * w;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= D * hw) return;
+  const int d = p / hw, pix = p - d * hw;
+  const int y = pix / w, x = pix - y * w;
+  // depth hypotheses: torch.linspace(depth_start, depth_end, D) (model.py:81-85; ATen's symmetric rule)
+  const float* cp = cam_params + ((size_t)(b * V) * 2 + 1) * 16 + 12;
+  const float dstart = cp[0], dint = cp[1];
+  const float dend = __fadd_rn(dstart, __fmul_rn((float)(D - 1), dint));  // model.py:67
+  const float step = D > 1 ? __fdiv_rn(__fsub_rn(dend, dstart), (float)(D - 1)) : 0.f;
+  const float depth = d < D / 2 ? __fadd_rn(dstart, __fmul_rn(step, (float)d))
+                                : __fsub_rn(dend, __fmul_rn(step, (float)(D - 1 - d)));
+  const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+  const float cx = __fsub_rn(__fmul_rn(dot3(cam + CB_KINV + 0, px, py, 1.f), depth), cam[CB_T0 + 0]);
+  const float cy = __fsub_rn(__fmul_rn(dot3(cam + CB_KINV + 3, px, py, 1.f), depth), cam[CB_T0 + 1]);
+  const float cz = __fsub_rn(__fmul_rn(dot3(cam + CB_KINV + 6, px, py, 1.f), depth), cam[CB_T0 + 2]);
+  const float wx = dot3(cam + CB_R0INV + 0, cx, cy, cz);
+  const float wy = dot3(cam + CB_R0INV + 3, cx, cy, cz);
+  const float wz = dot3(cam + CB_R0INV + 6, cx, cy, cz);
+  const float fV = (float)V;
+  const size_t plane = (size_t)hw;
+  for (int c0 = 0; c0 < C; c0 += CV_CH) {
+    float s1[CV_CH], s2[CV_CH];
+    const float* ref = feat + ((size_t)(b * V) * C + c0) * plane + pix;
+#pragma unroll
+    for (int c = 0; c < CV_CH; ++c) {
+      const float f0 = __ldg(ref + c * plane);
+      s1[c] = f0;
+      s2[c] = __fmul_rn(f0, f0);
+    }
+    for (int v = 1; v < V; ++v) {
+      const float* cv = cam + CB_VIEW + v * CB_VSTRIDE;
+      float u, vv;
+      project(cv, cv + 9, cv + 12, wx, wy, wz, u, vv);
+      const float ix = grid_coord(u, w), iy = grid_coord(vv, h);
+      const bool ok = usable(ix) && usable(iy);
+      const Taps tp = make_taps(ok ? ix : -10.f, ok ? iy : -10.f, w, h);
+      const float* m = feat + ((size_t)(b * V + v) * C + c0) * plane + (size_t)tp.y0 * w + tp.x0;
+#pragma unroll
+      for (int c = 0; c < CV_CH; ++c) {
+        const float* mc = m + c * plane;
+        float acc = 0.f;
+        if (tp.ok_n && tp.ok_w) acc = __fmul_rn(__ldg(mc), tp.nw);
+        if (tp.ok_n && tp.ok_e) acc = fmaf(__ldg(mc + 1), tp.ne, acc);
+        if (tp.ok_s && tp.ok_w) acc = fmaf(__ldg(mc + w), tp.sw, acc);
+        if (tp.ok_s && tp.ok_e) acc = fmaf(__ldg(mc + w + 1), tp.se, acc);
+        s1[c] = __fadd_rn(s1[c], acc);
+        s2[c] = __fadd_rn(s2[c], __fmul_rn(acc, acc));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CV_CH; ++c) {
+      const float a = __fdiv_rn(s1[c], fV);  // model.py:108-111, unfused
+      cost[(((size_t)b * C + c0 + c) * D + d) * plane + pix] = __fsub_rn(__fdiv_rn(s2[c], fV), __fmul_rn(a, a));
+    }
+  }
+}
+
 int launch_cam_setup(const float* cam_params, const float* interval, const float* mean, const float* stdv,
                      float* blocks, int B, int V, float kscale, float iscale, cudaStream_t st) {
   prof_begin("cam_setup", st);
@@ -554,4 +629,26 @@ extern "C" int pmvs_feature_fetch_backward(const float* grad_out, const float* p
   feature_fetch_kernel<true><<<grid, 256, 0, st>>>(nullptr, pts, intrinsics, extrinsics, const_cast<float*>(grad_out),
                                                    grad_maps, V, C, H, W, N);
   return check_launch("feature_fetch_backward_kernel");
+}
+
+extern "C" int pmvs_cost_volume(const float* features, const float* cam_params, float* cost, void* workspace,
+                                size_t workspace_bytes, int B, int V, int C, int h, int w, int D, int is_test,
+                                pmvs_stream_t stream) {
+  using namespace pmvs;
+  PMVS_REQUIRE(features && cam_params && cost && workspace, "cost_volume: NULL pointer");
+  PMVS_REQUIRE(B > 0 && B <= 65535 && V > 0 && V <= PMVS_MAX_VIEWS && h > 1 && w > 1 && D > 0, "cost_volume: bad shape");
+  PMVS_REQUIRE(C > 0 && C % CV_CH == 0, "cost_volume: channels must be a multiple of %d", CV_CH);
+  PMVS_REQUIRE((long long)D * h * w < (1ll << 31), "cost_volume: volume too large");
+  if (workspace_bytes < cam_block_bytes(B, V)) {
+    set_error("cost_volume: workspace %zu bytes < required %zu", workspace_bytes, cam_block_bytes(B, V));
+    return PMVS_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // model.py:58-61: K rows 0,1 divided by 2, and by 4 more at test time
+  PMVS_TRY(launch_cam_setup(cam_params, nullptr, nullptr, nullptr, (float*)workspace, B, V, is_test ? 0.125f : 0.5f, 1.f,
+                            st));
+  dim3 grid(cdiv((long long)D * h * w, 256), B);
+  prof_begin("cost_volume", st);
+  cost_volume_kernel<<<grid, 256, 0, st>>>(features, cam_params, (const float*)workspace, cost, V, C, h, w, D);
+  return check_launch("cost_volume_kernel", st);
 }

@@ -170,7 +170,7 @@ def gen_forward(sd):
         "mean": torch.tensor(DTU_MEAN).view(1, 3),
         "std": torch.tensor(DTU_STD).view(1, 3),
     }
-    cap = {"knn": [], "ec": [[], [], []], "mlp": [], "pyr": []}
+    cap = {"knn": [], "ec": [[], [], []], "mlp": [], "pyr": [], "coarse": [], "cost": []}
 
     orig_knn = ref_model.get_knn_3d
 
@@ -189,6 +189,10 @@ def gen_forward(sd):
         lambda mod, inp, out: cap["mlp"].append((inp[0].detach().clone(), out.detach().clone()))))
     hooks.append(net.flow_img_conv.register_forward_hook(
         lambda mod, inp, out: cap["pyr"].append({k: v.detach().clone() for k, v in out.items()})))
+    hooks.append(net.coarse_img_conv.register_forward_hook(
+        lambda mod, inp, out: cap["coarse"].append(out["conv3"].detach().clone())))
+    hooks.append(net.coarse_vol_conv.register_forward_pre_hook(
+        lambda mod, inp: cap["cost"].append(inp[0].detach().clone())))
     with torch.no_grad():
         preds = net(batch, (0.125, 0.25, 0.5), (1.0, 0.75, 0.15), isFlow=True, isTest=True)
     for h in hooks:
@@ -204,6 +208,10 @@ def gen_forward(sd):
          # every get_knn_3d result of the forward (21 calls), so the loop can be replayed
          # with the reference's own (implementation-defined) tie order
          knn_all=torch.stack([k for _, k in cap["knn"]], dim=0).to(torch.int16))
+    # coarse stage: per-view conv3 features and every 6th depth plane of the cost volume the
+    # reference feeds to VolumeConv (model.py:113-115)
+    save("coarse_small.npz", features=torch.stack(cap["coarse"], dim=1), cams=cams,
+         cost_planes=cap["cost"][0][:, :, ::6].contiguous(), plane_stride=np.array(6))
     # per-stage tensors: iteration 1 (one cloud) and the first sub-cloud of iteration 2
     st = {}
     for tag, call in (("it1", 0), ("it2", 1)):

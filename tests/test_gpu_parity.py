@@ -448,3 +448,30 @@ def test_ragged_shapes_six_views_vs_oracle(golden_params, golden_weights):
         assert torch.allclose(d_gpu, res, atol=5e-4, rtol=0), (it, (d_gpu - res).abs().max())
         assert torch.allclose(p_gpu, prob, atol=5e-5, rtol=0)
         depth = res
+
+
+def test_coarse_cost_volume_golden_and_oracle():
+    """(f-1) plane-sweep fetch + variance: against the cost volume the reference forward fed to
+    VolumeConv (every 6th plane, coarse_small.npz; tolerance 2e-5) and against the oracle on a
+    larger white-noise case with out-of-image projections.  White-noise features turn the fp32
+    rounding of the projected coordinate (a few 1e-5 px at coordinates ~50 px, CPU bmm vs the
+    kernel's FMA chain) directly into feature differences, so that case uses 2e-4 (measured:
+    2.3e-5 test mode, 7.1e-5 train mode where coordinates are 2x larger, on 0.03 % of the voxels)."""
+    from pointmvsnet_b200.cost_volume import build_cost_volume
+    from pointmvsnet_b200.synthetic import make_cameras
+    g = load_golden("coarse_small.npz")
+    cost = build_cost_volume(g["features"].to(DEV), g["cams"].to(DEV), is_test=True).cpu()
+    stride = int(g["plane_stride"])
+    assert tuple(cost.shape) == (1, 64, 48, 8, 16)
+    assert torch.allclose(cost[:, :, ::stride], g["cost_planes"], atol=2e-5, rtol=1e-5)
+    gen = torch.Generator().manual_seed(31)
+    feats = torch.randn(2, 5, 32, 20, 28, generator=gen)
+    cams = make_cameras(2, 5, 160, 224, 96)
+    want, _ = O.coarse_cost_volume(feats, cams, is_test=True)
+    got = build_cost_volume(feats.to(DEV), cams.to(DEV), is_test=True).cpu()
+    assert torch.allclose(got, want, atol=2e-4, rtol=1e-5), (got - want).abs().max()
+    assert ((got - want).abs() > 2e-5).float().mean() < 1e-3
+    want_t, _ = O.coarse_cost_volume(feats, cams, is_test=False)
+    got_t = build_cost_volume(feats.to(DEV), cams.to(DEV), is_test=False).cpu()
+    assert torch.allclose(got_t, want_t, atol=2e-4, rtol=1e-5), (got_t - want_t).abs().max()
+    assert ((got_t - want_t).abs() > 2e-5).float().mean() < 1e-3

@@ -88,3 +88,12 @@ def test_point_flow_pass_vs_reference(golden_params):
         err = (depth - rd).abs()
         assert err.max() < 2e-3, (i, err.max())  # mm, depths are ~650 mm (fp32 ulp 6e-5)
         assert (prob - rp).abs().max() < 1e-4
+
+
+def test_coarse_cost_volume_vs_reference():
+    """(f-1) plane-sweep fetch + variance of the coarse stage, model.py:54-113."""
+    g = load_golden("coarse_small.npz")
+    cost, depths = O.coarse_cost_volume(g["features"], g["cams"], is_test=True)
+    stride = int(g["plane_stride"])
+    assert torch.allclose(cost[:, :, ::stride], g["cost_planes"], atol=1e-6)
+    assert depths.shape[1] == 48
