@@ -222,8 +222,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its version banner / debug lines to stdout; keep stdout to ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "nccl_debug.%h.%p.log"))
+        # NCCL_DEBUG=VERSION (this image's default) makes NCCL print a banner on stdout; stdout must
+        # carry ONE JSON line, so the banner is switched off (any other explicit level is kept)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     H, W, V, D = CONFIGS[args.config]
     n_iter = len(IMG_SCALES)
@@ -448,10 +450,30 @@ def run_ours(args):
             "launches_per_step": int(launches_per_pass * G),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernel_table,
         }
-        print(json.dumps(line))
+        result_line = json.dumps(line)
+    else:
+        result_line = None
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return result_line
+
+
+class _StdoutToStderr(object):
+    """Route fd 1 to fd 2 while libraries (NCCL, CUDA, torchrun children) may chat; restore it
+    for the single JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -468,7 +490,10 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
     else:
-        run_ours(args)
+        with _StdoutToStderr():
+            line = run_ours(args)
+        if line is not None:
+            print(line, flush=True)
 
 
 if __name__ == "__main__":

@@ -176,6 +176,12 @@ class PointFlow(nn.Module):
         without a separate elementwise launch).  Returns (flow_result [B,1,h,w],
         flow_prob [B,5,h,w])."""
         require_cuda(estimated_depth_map, interval, cam_params_list, mean, std)
+        if not self.training:
+            # the reference runs inference under model.train() (test.py:58): BatchNorm uses batch
+            # statistics.  The fused path implements exactly that; running-statistics BN is only
+            # available through the stand-alone EdgeConv modules.
+            raise NotImplementedError("PointFlow implements the reference's inference mode (module.train(), "
+                                      "batch-statistics BatchNorm, test.py:58); call .train() on it")
         dev = estimated_depth_map.device
         if pyramids_channels_last is None:
             pyramids_channels_last = self.pyramids_to_channels_last(feature_pyramids)

@@ -475,3 +475,34 @@ def test_coarse_cost_volume_golden_and_oracle():
     got_t = build_cost_volume(feats.to(DEV), cams.to(DEV), is_test=False).cpu()
     assert torch.allclose(got_t, want_t, atol=2e-4, rtol=1e-5), (got_t - want_t).abs().max()
     assert ((got_t - want_t).abs() > 2e-5).float().mean() < 1e-3
+
+
+def test_edgeconv_generic_paths_runtime_k_and_simt_fallback():
+    """K != 16 (runtime-K gather loop), out_channels 16 (contraction falls back to the fp32 SIMT
+    kernel: the tcgen05 path covers N in {16, 64, 128}) and a ragged point count."""
+    from pointmvsnet_b200.networks import EdgeConv, EdgeConvNoC
+    gen = torch.Generator().manual_seed(41)
+    for cls, cin, cout, K, concat in ((EdgeConv, 16, 16, 8, True), (EdgeConvNoC, 24, 32, 5, False),
+                                      (EdgeConv, 64, 64, 16, True)):
+        B, N = 2, 333
+        x = torch.randn(B, cin, N, generator=gen)
+        idx = torch.randint(0, N, (B, N, K), generator=gen)
+        m = cls(cin, cout)
+        with torch.no_grad():
+            m.bn.weight.uniform_(0.5, 1.5); m.bn.bias.uniform_(-0.2, 0.2)
+        want = O.edge_conv(x, idx, m.conv1.weight.detach(), m.conv2.weight.detach(), m.bn.weight.detach(),
+                           m.bn.bias.detach(), concat)
+        m = m.to(DEV).train()
+        with torch.no_grad():
+            got = m(x.to(DEV), idx.to(DEV))
+        assert torch.allclose(got.cpu(), want, atol=2e-5, rtol=1e-4), (cls.__name__, (got.cpu() - want).abs().max())
+
+
+def test_point_flow_refuses_eval_mode(golden_weights):
+    pf = _pf(golden_weights).eval()
+    with pytest.raises(NotImplementedError):
+        pf(torch.zeros(1, 1, 8, 16, device=DEV), torch.ones(1, device=DEV), 0.125, 0,
+           feature_pyramids=[torch.zeros(1, 3, 16, 32, 64, device=DEV), torch.zeros(1, 3, 32, 16, 32, device=DEV),
+                             torch.zeros(1, 3, 64, 8, 16, device=DEV)],
+           cam_params_list=torch.zeros(1, 3, 2, 4, 4, device=DEV), mean=torch.zeros(1, 3, device=DEV),
+           std=torch.ones(1, 3, device=DEV))
