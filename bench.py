@@ -368,6 +368,7 @@ def run_ours(args):
 
     # ---- per-kernel CUDA-event timing (eager, not captured) for the roofline ---------------
     roofline = None
+    roofline_gemm = None
     kernel_table = None
     if rank == 0:
         with torch.no_grad():
@@ -407,9 +408,28 @@ def run_ours(args):
         for name, (ms, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             per_pass_ms = ms / reps
             ab = alg.get(name, (0, 0))[0]
+            gbps = ab / (per_pass_ms * 1e-3) / 1e9 if per_pass_ms > 0 else None
             kernel_table[name] = {"ms_per_pass": round(per_pass_ms, 5), "share": round(ms / tot, 4),
                                   "launches_per_pass": cnt // reps,
-                                  "alg_GBps": round(ab / (per_pass_ms * 1e-3) / 1e9, 1) if per_pass_ms > 0 else None}
+                                  "alg_GBps": round(gbps, 1) if gbps is not None else None,
+                                  "hbm_frac": round(gbps / hbm_peak, 4) if gbps is not None else None}
+        # tensor-pipe view of the contraction kernels: executed TF32 FLOPs (3 products per element
+        # for 3xTF32) over their summed time, against half the measured dense bf16 GEMM rate
+        # (kind::tf32 runs at half the bf16 rate; MEASURED_PEAKS.json has no TF32 figure)
+        gemm_ms = sum(ms for name, (ms, cnt) in agg.items() if name.startswith("gemm_")) / reps
+        mac_per_pt = 136 * 64 + 32 * 64 + 64 * 128 + 224 * 64 + 64 * 64 + 64 * 16
+        pts = sum(5 * int(H * sc) * int(W * sc) for sc in IMG_SCALES)
+        mode = _lib.lib.pmvs_get_gemm_mode()
+        flops = 2.0 * mac_per_pt * pts * (3 if mode == 3 else 1)
+        tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+        roofline_gemm = None
+        if gemm_ms > 0 and mode != 0:
+            ach = flops / (gemm_ms * 1e-3) / 1e12
+            roofline_gemm = {"kernels": "gemm_* (tcgen05 kind::tf32, mode %d)" % mode, "bound": "tensor",
+                             "achieved": round(ach, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                             "frac": round(ach / tf32_peak, 4), "ms_per_pass": round(gemm_ms, 4),
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)",
+                             "note": "the contractions are memory bound (25 FLOP/B): see kernels[*].alg_GBps"}
         dom = max(agg.items(), key=lambda kv: kv[1][0])[0]
         dom_ms_per_launch = agg[dom][0] / agg[dom][1]
         dom_bytes_per_launch = alg.get(dom, (0, 1))[0] / max(1, alg.get(dom, (0, 1))[1])
@@ -448,7 +468,8 @@ def run_ours(args):
                            "inside every timed step"},
             "gpu_launches": int(launches_per_pass * G * args.steps),
             "launches_per_step": int(launches_per_pass * G),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernel_table,
+            "clocks": clocks, "roofline": roofline, "roofline_gemm": roofline_gemm, "cpu_baseline": cpu_baseline,
+            "kernels": kernel_table,
         }
         result_line = json.dumps(line)
     else:
