@@ -70,9 +70,8 @@ def algorithmic_bytes_per_pass(H, W, V, B=1):
         h, w = int(H * s), int(W * s)
         P = h * w * B
         R = 5 * P
-        for c, (hh, ww) in zip((16, 32, 64), ((H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8))):
-            if hh > h or ww > w:  # level down-sampled to the flow resolution once per iteration
-                add("resize_down", B * V * c * 4 * (hh * ww + h * w))
+        # model.py:184 materialised once per iteration: read the pyramids, write [B,V,h,w,112] fp32
+        add("warp_source", pyr_bytes + B * V * h * w * 448)
         add("fused_fetch", pyr_bytes + 4 * prev * B + 2720 * P + 60 * P)
         add("knn3d", R * (12 + 64))
         for (cin, cout2, c) in ((136, 64, 32), (32, 64, 32), (64, 128, 64)):

@@ -80,52 +80,6 @@ int launch_transpose(const float* in, float* out, int batch, int R, int C, cudaS
   return check_launch("transpose_kernel", st);
 }
 
-// bilinear resize of a channels-last map, F.interpolate(mode="bilinear", align_corners=False)
-// (model.py:184; ATen upsample_bilinear2d source-index rule).  One thread per output float4.
-__global__ void __launch_bounds__(256)
-    resize_cl_kernel(const float* __restrict__ in, float* __restrict__ out, int C4, int hi, int wi, int ho, int wo,
-                     long long total) {
-  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const int c4 = (int)(e % C4);
-  long long t = e / C4;
-  const int x = (int)(t % wo);
-  t /= wo;
-  const int y = (int)(t % ho);
-  const long long bv = t / ho;
-  const float sy = (float)hi / (float)ho, sx = (float)wi / (float)wo;
-  float fy = __fsub_rn(__fmul_rn(sy, (float)y + 0.5f), 0.5f), fx = __fsub_rn(__fmul_rn(sx, (float)x + 0.5f), 0.5f);
-  fy = fy < 0.f ? 0.f : fy;
-  fx = fx < 0.f ? 0.f : fx;
-  int y0 = (int)fy, x0 = (int)fx;
-  y0 = y0 > hi - 1 ? hi - 1 : y0;
-  x0 = x0 > wi - 1 ? wi - 1 : x0;
-  const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
-  const float ly1 = __fsub_rn(fy, (float)y0), ly0 = __fsub_rn(1.f, ly1);
-  const float lx1 = __fsub_rn(fx, (float)x0), lx0 = __fsub_rn(1.f, lx1);
-  const float* base = in + bv * (long long)hi * wi * C4 * 4 + c4 * 4;
-  const float4 v00 = ldg4(base + ((long long)y0 * wi + x0) * C4 * 4), v01 = ldg4(base + ((long long)y0 * wi + x1) * C4 * 4);
-  const float4 v10 = ldg4(base + ((long long)y1 * wi + x0) * C4 * 4), v11 = ldg4(base + ((long long)y1 * wi + x1) * C4 * 4);
-  float4 o;  // h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11), ATen's association
-  o.x = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.x), __fmul_rn(lx1, v01.x))),
-                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.x), __fmul_rn(lx1, v11.x))));
-  o.y = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.y), __fmul_rn(lx1, v01.y))),
-                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.y), __fmul_rn(lx1, v11.y))));
-  o.z = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.z), __fmul_rn(lx1, v01.z))),
-                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.z), __fmul_rn(lx1, v11.z))));
-  o.w = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.w), __fmul_rn(lx1, v01.w))),
-                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.w), __fmul_rn(lx1, v11.w))));
-  st4(out + e * 4, o);
-}
-
-int launch_resize_cl(const float* in, float* out, int BV, int C, int hi, int wi, int ho, int wo, cudaStream_t st) {
-  const long long total = (long long)BV * ho * wo * (C / 4);
-  PMVS_REQUIRE(C % 4 == 0 && total > 0 && cdiv(total, 256) < (1ll << 31), "resize: bad shape");
-  prof_begin("resize_down", st);
-  resize_cl_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(in, out, C / 4, hi, wi, ho, wo, total);
-  return check_launch("resize_cl_kernel", st);
-}
-
 __global__ void idx_convert_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = (int32_t)in[i];
@@ -172,8 +126,7 @@ struct FlowPlan {
   int S, hs, ws, N;
   size_t R;  // rows = S * B * N
   size_t cam, feature, xyz, idx, le, ecat, h0, h1, h2, stats, total;
-  size_t resized[3];   // per pyramid level: offset of the materialised down-sampled copy, or 0 if unused
-  bool downsample[3];
+  size_t warp_src;     // the pyramid levels resized to the flow grid, [B,V,h,w,112]
   size_t st_ec[3], st_mlp[3];  // offsets (in doubles) inside the stats region
   size_t stats_doubles;
 };
@@ -204,14 +157,7 @@ static int make_plan(const pmvs_flow_shape* s, FlowPlan& p) {
   p.h0 = o; o += align_up(p.R * 64 * 4);
   p.h1 = o; o += align_up(p.R * 64 * 4);
   p.h2 = o; o += align_up(p.R * 16 * 4);
-  for (int l = 0; l < 3; ++l) {
-    // a level larger than the flow resolution is DOWN-sampled by the reference (model.py:184); the
-    // small resized map is materialised once per iteration (then sampled with 4 taps) instead of
-    // composing 4 x 4 native taps per sample
-    p.downsample[l] = s->pyr_h[l] > s->flow_h || s->pyr_w[l] > s->flow_w;
-    p.resized[l] = 0;
-    if (p.downsample[l]) { p.resized[l] = o; o += align_up((size_t)s->B * s->V * s->flow_h * s->flow_w * (16 << l) * 4); }
-  }
+  p.warp_src = o; o += align_up(warp_source_bytes(s->B, s->V, s->flow_h, s->flow_w));
   size_t d = 0;
   const int ec_cout[3] = {32, 32, 64};
   const int mlp_cout[3] = {64, 64, 16};
@@ -397,16 +343,12 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
   const float kscale = shape->is_test ? shape->image_scale : (float)(4.0 * (double)shape->image_scale);
   PMVS_TRY(launch_cam_setup(cam_params, interval, mean, stdv, cam, B, shape->V, kscale, shape->interval_scale, st));
 
+  // model.py:184: every level of every view resized to the flow grid, once per iteration
+  float* warp_src = (float*)(ws + p.warp_src);
+  PMVS_TRY(launch_warp_source(pyramids_cl, shape->pyr_h, shape->pyr_w, warp_src, B * shape->V, shape->flow_h,
+                              shape->flow_w, st));
   FusedFetchParams f{};
-  for (int l = 0; l < 3; ++l) {
-    f.pyr[l] = pyramids_cl[l]; f.hl[l] = shape->pyr_h[l]; f.wl[l] = shape->pyr_w[l];
-    if (p.downsample[l]) {
-      float* rz = (float*)(ws + p.resized[l]);
-      PMVS_TRY(launch_resize_cl(pyramids_cl[l], rz, B * shape->V, 16 << l, shape->pyr_h[l], shape->pyr_w[l],
-                                shape->flow_h, shape->flow_w, st));
-      f.pyr[l] = rz; f.hl[l] = shape->flow_h; f.wl[l] = shape->flow_w;
-    }
-  }
+  f.src = warp_src;
   f.depth_prev = depth_prev; f.cam_blocks = cam; f.feature = feature; f.xyz = xyz;
   f.B = B; f.V = shape->V; f.h = shape->flow_h; f.w = shape->flow_w; f.hp = shape->prev_h; f.wp = shape->prev_w;
   f.ratio = shape->ratio;

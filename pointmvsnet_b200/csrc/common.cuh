@@ -109,14 +109,18 @@ int launch_edge_stats(const EdgeArgs& a, cudaStream_t st);
 int launch_edge_apply(const EdgeArgs& a, cudaStream_t st);
 
 struct FusedFetchParams {
-  const float* pyr[3];  // channels-last [B,V,hl,wl,C]
-  int hl[3], wl[3];
+  const float* src;         // warp source map [B,V,h,w,112]: the pyramid levels resized to the flow grid
   const float* depth_prev;  // [B,1,hp,wp]
   const float* cam_blocks;  // [B, cam_block_floats(V)]
   float* feature;           // [S,B,N,136]
   float* xyz;               // [S,B,3,N]
   int B, V, h, w, hp, wp, ratio;
+  int ppw;                  // pixels per warp (set by the launcher)
 };
+// model.py:184 for the three levels at once: channels-last pyramids [B*V,hl,wl,16<<l] -> [B*V,h,w,112]
+int launch_warp_source(const float* const pyr[3], const int hl[3], const int wl[3], float* out, int BV, int h, int w,
+                       cudaStream_t st);
+size_t warp_source_bytes(int B, int V, int h, int w);
 int launch_cam_setup(const float* cam_params, const float* interval, const float* mean, const float* stdv,
                      float* blocks, int B, int V, float kscale, float iscale, cudaStream_t st);
 int launch_fused_fetch(const FusedFetchParams& p, cudaStream_t st);

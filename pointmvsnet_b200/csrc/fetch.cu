@@ -2,13 +2,13 @@
 //
 //  (1) pmvs_feature_fetch*: the stand-alone FeatureFetcher operator
 //      (reference utils/feature_fetcher.py:13-60), generic C / NCHW.
-//  (2) fused_fetch_kernel: rows a2-a9 of the hot path (reference model.py:153-204) in one
-//      launch: nearest depth upsample, pixel grid, hypothesis un-projection, projection into
-//      every view, pyramid resize composed with the bilinear fetch, variance over views,
-//      xyz normalisation, and the 136-channel point feature written points-major in the
-//      sub-cloud order the EdgeConv kernels consume.  One warp owns one pixel: lanes span
-//      the 112 pyramid channels (16 lanes x float4 on conv3, 8 on conv2, 4 on conv1), so a
-//      tap is one fully used 256/128/64-byte segment of the channels-last pyramid.
+//  (2) warp_source_kernel + fused_fetch_kernel: rows a2-a9 of the hot path (reference
+//      model.py:153-204): pyramid resize to the flow grid (all levels into one channels-last
+//      112-channel map), then in one launch nearest depth upsample, pixel grid, hypothesis
+//      un-projection, projection into every view, bilinear fetch, variance over views, xyz
+//      normalisation, and the 136-channel point feature written points-major in the sub-cloud
+//      order the EdgeConv kernels consume.  One warp owns a pixel at a time: 28 lanes span the
+//      112 pyramid channels as float4s, so a tap is one contiguous 448-byte read.
 //      Camera matrices for the CTA's batch element are staged into shared memory with one
 //      cp.async.bulk (TMA bulk copy) completing on an mbarrier.
 #include "common.cuh"
@@ -193,156 +193,93 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------
-// (2) fused warp + fetch + variance
+// (2) warp source map + fused warp / fetch / variance
 // ---------------------------------------------------------------------------------------
+// model.py:184 resizes every pyramid level of every view to the flow resolution
+// (F.interpolate, bilinear, align_corners=False) before sampling it.  warp_source_kernel
+// does exactly that, ONCE per iteration, for the three levels together, into one
+// channels-last map [B, V, h, w, 112] (conv1 16 | conv2 32 | conv3 64 channels): all levels
+// then share the sample positions and bilinear weights of a projected point, a tap is one
+// contiguous 448-byte read, and a sample costs 4 taps whatever the scale factor.  (An earlier
+// version composed resize and sampling on the native maps to save these bytes; it needed ~9 taps
+// per sample and per-level descriptors, and the kernel was instruction-issue bound at 9 % of the
+// HBM roofline - see DESIGN.md 3.1.)  One thread per output float4; ATen's
+// upsample_bilinear2d source-index rule and association.
+constexpr int FETCH_CH = 112;        // pyramid channels per source texel
+constexpr int FETCH_C4 = FETCH_CH / 4;
 
-// One axis of "bilinear sample of the bilinearly resized map" as <= 4 (index, weight)
-// pairs into the NATIVE map.  The resized map (F.interpolate, align_corners=False,
-// model.py:184) is never materialised: tap r of the sampled map is
-//   l0 * native[p0] + l1 * native[p1]   (ATen upsample_bilinear2d source index rule)
-// and the two sample taps (floor, floor+1) carry the grid_sample weights
-// (ATen grid_sampler_2d, zeros padding: out-of-range taps contribute nothing).
-// Duplicate native indices are folded and the non-zero entries are compacted to the front,
-// so the consumer loops stop at the first zero weight.
-struct Axis {
-  int i[4];
-  float w[4];
+struct WarpSourceParams {
+  const float* pyr[3];  // channels-last [B*V, hl, wl, 16 << l]
+  int hl[3], wl[3];
+  float* out;           // [B*V, h, w, 112]
+  int h, w;
+  long long total;      // float4 elements
 };
-__device__ __forceinline__ void axis_entries(float coord, int out_size, int in_size, float scale, bool valid,
-                                             Axis& a) {
-  const float f = floorf(coord);
-  const int r0 = (int)f;
-  const float wt[2] = {__fsub_rn(f + 1.f, coord), __fsub_rn(coord, f)};
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const int r = r0 + s;
-    const bool inb = valid && r >= 0 && r < out_size;
-    float src = __fsub_rn(__fmul_rn(scale, (float)r + 0.5f), 0.5f);
-    if (src < 0.f) src = 0.f;
-    int p0 = (int)src;
-    if (p0 > in_size - 1) p0 = in_size - 1;
-    const int p1 = p0 + (p0 < in_size - 1 ? 1 : 0);
-    const float l1 = __fsub_rn(src, (float)p0);
-    const float l0 = __fsub_rn(1.f, l1);
-    a.i[2 * s] = p0;
-    a.i[2 * s + 1] = p1;
-    a.w[2 * s] = inb ? __fmul_rn(wt[s], l0) : 0.f;
-    a.w[2 * s + 1] = inb ? __fmul_rn(wt[s], l1) : 0.f;
-  }
-  // fold duplicate native indices so every native texel is loaded once
-  if (a.i[1] == a.i[0]) { a.w[0] += a.w[1]; a.w[1] = 0.f; }
-  if (a.i[3] == a.i[2]) { a.w[2] += a.w[3]; a.w[3] = 0.f; }
-  if (a.i[2] == a.i[0]) { a.w[0] += a.w[2]; a.w[2] = 0.f; }
-  else if (a.i[2] == a.i[1]) { a.w[1] += a.w[2]; a.w[2] = 0.f; }
-  if (a.i[3] == a.i[1]) { a.w[1] += a.w[3]; a.w[3] = 0.f; }
-  else if (a.i[3] == a.i[0]) { a.w[0] += a.w[3]; a.w[3] = 0.f; }
-  // compaction: bubble zero weights to the back (stable for the non-zero entries)
-#pragma unroll
-  for (int pass = 0; pass < 3; ++pass) {
-#pragma unroll
-    for (int j = 0; j < 3 - pass; ++j) {
-      const bool sw = a.w[j] == 0.f;
-      const float tw = a.w[j];
-      const int ti = a.i[j];
-      a.w[j] = sw ? a.w[j + 1] : tw;
-      a.i[j] = sw ? a.i[j + 1] : ti;
-      a.w[j + 1] = sw ? tw : a.w[j + 1];
-      a.i[j + 1] = sw ? ti : a.i[j + 1];
-    }
-  }
+
+__global__ void __launch_bounds__(256) warp_source_kernel(const WarpSourceParams p) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= p.total) return;
+  const int c4 = (int)(e % FETCH_C4);
+  long long t = e / FETCH_C4;
+  const int x = (int)(t % p.w);
+  t /= p.w;
+  const int y = (int)(t % p.h);
+  const long long bv = t / p.h;
+  const int l = c4 < 4 ? 0 : (c4 < 12 ? 1 : 2);
+  const int cq = c4 - (l == 0 ? 0 : (l == 1 ? 4 : 12));
+  const int C4 = 4 << l;
+  const int hi = l == 0 ? p.hl[0] : (l == 1 ? p.hl[1] : p.hl[2]);  // (no dynamic indexing of the parameter struct)
+  const int wi = l == 0 ? p.wl[0] : (l == 1 ? p.wl[1] : p.wl[2]);
+  const float* lvl = l == 0 ? p.pyr[0] : (l == 1 ? p.pyr[1] : p.pyr[2]);
+  const float sy = (float)hi / (float)p.h, sx = (float)wi / (float)p.w;  // area_pixel_compute_scale
+  float fy = __fsub_rn(__fmul_rn(sy, (float)y + 0.5f), 0.5f), fx = __fsub_rn(__fmul_rn(sx, (float)x + 0.5f), 0.5f);
+  fy = fy < 0.f ? 0.f : fy;
+  fx = fx < 0.f ? 0.f : fx;
+  int y0 = (int)fy, x0 = (int)fx;
+  y0 = y0 > hi - 1 ? hi - 1 : y0;
+  x0 = x0 > wi - 1 ? wi - 1 : x0;
+  const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
+  const float ly1 = __fsub_rn(fy, (float)y0), ly0 = __fsub_rn(1.f, ly1);
+  const float lx1 = __fsub_rn(fx, (float)x0), lx0 = __fsub_rn(1.f, lx1);
+  const float* base = lvl + bv * (long long)hi * wi * C4 * 4 + cq * 4;
+  const float4 v00 = ldg4(base + ((long long)y0 * wi + x0) * C4 * 4), v01 = ldg4(base + ((long long)y0 * wi + x1) * C4 * 4);
+  const float4 v10 = ldg4(base + ((long long)y1 * wi + x0) * C4 * 4), v11 = ldg4(base + ((long long)y1 * wi + x1) * C4 * 4);
+  float4 o;  // h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11), ATen's association
+  o.x = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.x), __fmul_rn(lx1, v01.x))),
+                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.x), __fmul_rn(lx1, v11.x))));
+  o.y = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.y), __fmul_rn(lx1, v01.y))),
+                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.y), __fmul_rn(lx1, v11.y))));
+  o.z = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.z), __fmul_rn(lx1, v01.z))),
+                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.z), __fmul_rn(lx1, v11.z))));
+  o.w = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.w), __fmul_rn(lx1, v01.w))),
+                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.w), __fmul_rn(lx1, v11.w))));
+  st4(p.out + e * 4, o);
 }
 
 constexpr int FETCH_WARPS = 8;
-constexpr int FETCH_TRIPLES_PER_ROUND = 10;  // 30 lanes build 10 (hypothesis, view) triples of level descriptors
 
-// Sampling descriptor of one (hypothesis, view, level): element offsets (already multiplied
-// by the channel count / row pitch) and weights per axis, plus the loop bounds shared by the
-// axis tap counts (the tap loops run to the warp-wide maximum of the step).
+// Sampling descriptor of one (hypothesis, view): byte offsets of the NW, NE, SW, SE texels inside
+// the view's [h, w, 112] map and their grid_sample weights.  Out-of-range taps (zeros padding)
+// carry weight 0 and offset 0, so the consumer runs 4 unconditional taps: fma(t, 0, acc) == acc.
 struct __align__(16) Desc {
-  unsigned xo[4];   // byte offsets of the native texels along x (index * C * 4)
-  float xw[4];
-  unsigned yo[4];   // byte offsets of (view, row)
-  float yw[4];
-  int nx, ny, pad0, pad1;
+  unsigned o[4];
+  float w[4];
 };
-static_assert(sizeof(Desc) == 80, "Desc layout");
+static_assert(sizeof(Desc) == 32, "Desc layout");
 
 __host__ __device__ constexpr size_t fetch_smem_bytes(int V) {  // descriptors
-  return (size_t)FETCH_WARPS * PMVS_NUM_HYP * V * 3 * sizeof(Desc);
+  return (size_t)FETCH_WARPS * PMVS_NUM_HYP * V * sizeof(Desc);
 }
 __host__ __device__ constexpr size_t fetch_smem_total(int V) {  // + 16 floats of xyz per warp
   return fetch_smem_bytes(V) + FETCH_WARPS * 16 * sizeof(float);
 }
 
-// One pyramid level L (0: conv1 16 ch, 1: conv2 32 ch, 2: conv3 64 ch) for the 5 hypotheses of a
-// pixel; see "phase 2" in fused_fetch_kernel.  A level with C channels needs C/4 lanes per sample,
-// so 32/(C/4) HYPOTHESES are sampled side by side (2 on conv3, 4 on conv2, 8 >= 5 on conv1) and the
-// views are walked sequentially: every lane owns its hypothesis' running sum / sum of squares in
-// view order (model.py:188-189) and no cross-lane reduction is needed.  The hypotheses of a pixel
-// project to nearly the same place in a view, so their tap counts agree and the warp-uniform
-// loop bounds are tight.
-template <int L>
-__device__ __forceinline__ void level_pass(const FusedFetchParams& p, const Desc* desc, int b, int V, int lane,
-                                           float rV, float* frow0, size_t fstep) {
-  constexpr int C = 16 << L;
-  constexpr int G = C / 4;        // lanes per sample
-  constexpr int S = 32 / G;       // hypotheses sampled per step
-  constexpr int CH_OFF = L == 2 ? 48 : (L == 1 ? 16 : 0);
-  const int grp = lane / G, cq = lane % G;
-  const char* lbase = reinterpret_cast<const char*>(p.pyr[L] + cq * 4 + (size_t)b * V * p.hl[L] * p.wl[L] * C);
-#pragma unroll 1
-  for (int m0 = 0; m0 < PMVS_NUM_HYP; m0 += S) {
-    const int m = m0 + grp;
-    const bool active = m < PMVS_NUM_HYP;
-    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-#pragma unroll 1
-    for (int v = 0; v < V; ++v) {
-      Desc dd = desc[((active ? m : 0) * V + v) * 3 + L];
-      if (!active) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { dd.xw[j] = 0.f; dd.yw[j] = 0.f; }
-        dd.nx = 0; dd.ny = 0;
-      }
-      const int nxm = __reduce_max_sync(0xffffffffu, dd.nx);
-      const int nym = __reduce_max_sync(0xffffffffu, dd.ny);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int ey = 0; ey < 4; ++ey) {
-        if (ey < nym) {  // warp-uniform bound
-          const char* row = lbase + dd.yo[ey];
-#pragma unroll
-          for (int ex = 0; ex < 4; ++ex) {
-            if (ex < nxm) {  // warp-uniform bound
-              const float wgt = __fmul_rn(dd.yw[ey], dd.xw[ex]);
-              const float4 t = __ldg(reinterpret_cast<const float4*>(row + dd.xo[ex]));
-              acc.x = fmaf(wgt, t.x, acc.x);
-              acc.y = fmaf(wgt, t.y, acc.y);
-              acc.z = fmaf(wgt, t.z, acc.z);
-              acc.w = fmaf(wgt, t.w, acc.w);
-            }
-          }
-        }
-      }
-      // model.py:188-189: sums over views of x and x**2, in view order
-      s1.x = __fadd_rn(s1.x, acc.x); s1.y = __fadd_rn(s1.y, acc.y);
-      s1.z = __fadd_rn(s1.z, acc.z); s1.w = __fadd_rn(s1.w, acc.w);
-      s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
-      s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
-    }
-    if (active) {
-      // model.py:190: mean(x^2) - mean(x)^2 (difference unfused); mean = sum * (1/V) as ATen's
-      // CUDA mean kernel computes it (identical to sum / V for V a power of two)
-      float4 o;
-      float a;
-      a = __fmul_rn(s1.x, rV); o.x = __fsub_rn(__fmul_rn(s2.x, rV), __fmul_rn(a, a));
-      a = __fmul_rn(s1.y, rV); o.y = __fsub_rn(__fmul_rn(s2.y, rV), __fmul_rn(a, a));
-      a = __fmul_rn(s1.z, rV); o.z = __fsub_rn(__fmul_rn(s2.z, rV), __fmul_rn(a, a));
-      a = __fmul_rn(s1.w, rV); o.w = __fsub_rn(__fmul_rn(s2.w, rV), __fmul_rn(a, a));
-      st4(frow0 + m * fstep + CH_OFF + cq * 4, o);
-    }
-  }
-}
-
+// rows a2-a9 for p.ppw consecutive pixels per warp.  Phase 1: lane t = (hypothesis m, view v)
+// un-projects the hypothesis, projects it into the view and writes the 4-tap descriptor.  Phase 2:
+// lanes 0..27 each own one float4 of the 112 channels; for every hypothesis the views are walked in
+// order and the lane keeps the sum / sum of squares of its channels (model.py:188-189), so there
+// is no cross-lane reduction; one tap = one 128-bit ld.global.nc + 4 FFMA per lane, 448 contiguous
+// bytes per warp.
 __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const FusedFetchParams p) {
   __shared__ __align__(16) float cam[cam_block_floats(PMVS_MAX_VIEWS)];
   __shared__ __align__(8) unsigned long long bar;
@@ -381,116 +318,144 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pix = blockIdx.x * FETCH_WARPS + warp;
   const int h = p.h, w = p.w;
-  if (pix >= h * w) return;  // warp-uniform
-  const int Y = pix / w, X = pix - Y * w;
-  const int ntriples = PMVS_NUM_HYP * V;
-  Desc* desc = reinterpret_cast<Desc*>(dyn_smem) + (size_t)warp * ntriples * 3;
-
-  // nearest upsample of the previous depth (model.py:153-158; ATen nearest index rule)
-  const float nsy = (float)p.hp / (float)h, nsx = (float)p.wp / (float)w;
-  int ys = (int)floorf((float)Y * nsy), xs = (int)floorf((float)X * nsx);
-  ys = ys < p.hp - 1 ? ys : p.hp - 1;
-  xs = xs < p.wp - 1 ? xs : p.wp - 1;
-  const float dprev = __ldg(p.depth_prev + ((size_t)b * p.hp + ys) * p.wp + xs);
-
-  // uv = K_ref^-1 * (x + .5, y + .5, 1)   (functions.py:128-138, model.py:165-170)
-  const float px = (float)X + 0.5f, py = (float)Y + 0.5f;
-  const float uvx = dot3(cam + CB_KINV + 0, px, py, 1.f);
-  const float uvy = dot3(cam + CB_KINV + 3, px, py, 1.f);
-  const float uvz = dot3(cam + CB_KINV + 6, px, py, 1.f);
+  const int npair = PMVS_NUM_HYP * V;
+  Desc* desc = reinterpret_cast<Desc*>(dyn_smem) + (size_t)warp * npair;
+  float* xyzs = reinterpret_cast<float*>(dyn_smem + fetch_smem_bytes(V)) + warp * 16;
   const float interval = cam[CB_INTERVAL];
+  const float nsy = (float)p.hp / (float)h, nsx = (float)p.wp / (float)w;
+  const int r = p.ratio;
+  const int hs = h / r, wsub = w / r;
+  const int Npts = PMVS_NUM_HYP * hs * wsub;
+  const float rV = __frcp_rn((float)V);
+  const size_t fstep = (size_t)hs * wsub * PMVS_FEAT_CH;  // next hypothesis
+  const size_t vstride = (size_t)h * w * FETCH_CH * sizeof(float);
+  const char* src0 = reinterpret_cast<const char*>(p.src) + (size_t)b * V * vstride + lane * 16;
 
-  auto world_point = [&](int m, float& wx, float& wy, float& wz) {
-    const float dm = __fadd_rn(dprev, __fmul_rn(interval, (float)(m - 2)));  // model.py:174
-    const float cx = __fsub_rn(__fmul_rn(uvx, dm), cam[CB_T0 + 0]);
-    const float cy = __fsub_rn(__fmul_rn(uvy, dm), cam[CB_T0 + 1]);
-    const float cz = __fsub_rn(__fmul_rn(uvz, dm), cam[CB_T0 + 2]);
-    wx = dot3(cam + CB_R0INV + 0, cx, cy, cz);  // model.py:177
-    wy = dot3(cam + CB_R0INV + 3, cx, cy, cz);
-    wz = dot3(cam + CB_R0INV + 6, cx, cy, cz);
-  };
+  const int pix0 = (blockIdx.x * FETCH_WARPS + warp) * p.ppw;
+  for (int k = 0; k < p.ppw; ++k) {
+    const int pix = pix0 + k;
+    if (pix >= h * w) break;  // warp-uniform
+    const int Y = pix / w, X = pix - Y * w;
 
-  // ---- phase 1: 30 lanes build the (hypothesis, view, level) sampling descriptors ----------
-  {
-    const int tl = lane / 3, l = lane - tl * 3;  // triple inside the round, level
-    const int hl = lane < 30 ? p.hl[l] : 1, wl = lane < 30 ? p.wl[l] : 1;
-    const int Cl = 16 << l;
-    const float sxl = (float)wl / (float)w, syl = (float)hl / (float)h;  // ATen area_pixel_compute_scale
-    for (int t0 = 0; t0 < ntriples; t0 += FETCH_TRIPLES_PER_ROUND) {
-      const int t = t0 + tl;
-      const bool act = lane < 30 && t < ntriples;
-      const int m = act ? t / V : 0, v = act ? t - m * V : 0;
+    // nearest upsample of the previous depth (model.py:153-158; ATen nearest index rule)
+    int ys = (int)floorf((float)Y * nsy), xs = (int)floorf((float)X * nsx);
+    ys = ys < p.hp - 1 ? ys : p.hp - 1;
+    xs = xs < p.wp - 1 ? xs : p.wp - 1;
+    const float dprev = __ldg(p.depth_prev + ((size_t)b * p.hp + ys) * p.wp + xs);
+
+    // uv = K_ref^-1 * (x + .5, y + .5, 1)   (functions.py:128-138, model.py:165-170)
+    const float px = (float)X + 0.5f, py = (float)Y + 0.5f;
+    const float uvx = dot3(cam + CB_KINV + 0, px, py, 1.f);
+    const float uvy = dot3(cam + CB_KINV + 3, px, py, 1.f);
+    const float uvz = dot3(cam + CB_KINV + 6, px, py, 1.f);
+
+    auto world_point = [&](int m, float& wx, float& wy, float& wz) {
+      const float dm = __fadd_rn(dprev, __fmul_rn(interval, (float)(m - 2)));  // model.py:174
+      const float cx = __fsub_rn(__fmul_rn(uvx, dm), cam[CB_T0 + 0]);
+      const float cy = __fsub_rn(__fmul_rn(uvy, dm), cam[CB_T0 + 1]);
+      const float cz = __fsub_rn(__fmul_rn(uvz, dm), cam[CB_T0 + 2]);
+      wx = dot3(cam + CB_R0INV + 0, cx, cy, cz);  // model.py:177
+      wy = dot3(cam + CB_R0INV + 3, cx, cy, cz);
+      wz = dot3(cam + CB_R0INV + 6, cx, cy, cz);
+    };
+
+    // ---- phase 1: one lane per (hypothesis, view) builds its sampling descriptor --------------
+    for (int t = lane; t < npair; t += 32) {
+      const int m = t / V, v = t - m * V;
       float wx, wy, wz;
       world_point(m, wx, wy, wz);
       const float* cv = cam + CB_VIEW + v * CB_VSTRIDE;
       float u, vv;
       project(cv, cv + 9, cv + 12, wx, wy, wz, u, vv);
       const float ix = grid_coord(u, w), iy = grid_coord(vv, h);
-      const bool ok = act && usable(ix) && usable(iy);
-      Axis ax, ay;
-      axis_entries(ok ? ix : 0.f, w, wl, sxl, ok, ax);
-      axis_entries(ok ? iy : 0.f, h, hl, syl, ok, ay);
-      int nx = (ax.w[0] != 0.f) + (ax.w[1] != 0.f) + (ax.w[2] != 0.f) + (ax.w[3] != 0.f);
-      int ny = (ay.w[0] != 0.f) + (ay.w[1] != 0.f) + (ay.w[2] != 0.f) + (ay.w[3] != 0.f);
-      if (act) {
-        Desc dd;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dd.xo[j] = (unsigned)(ax.i[j] * Cl) * 4u;
-          dd.xw[j] = ax.w[j];
-          dd.yo[j] = (unsigned)((ay.i[j] + v * hl) * wl * Cl) * 4u;
-          dd.yw[j] = ay.w[j];
+      const bool ok = usable(ix) && usable(iy);
+      const Taps tp = make_taps(ok ? ix : -10.f, ok ? iy : -10.f, w, h);
+      const bool k00 = tp.ok_n && tp.ok_w, k01 = tp.ok_n && tp.ok_e, k10 = tp.ok_s && tp.ok_w, k11 = tp.ok_s && tp.ok_e;
+      const unsigned o00 = (unsigned)(tp.y0 * w + tp.x0) * (unsigned)(FETCH_CH * 4);
+      Desc dd;
+      dd.o[0] = k00 ? o00 : 0u;
+      dd.o[1] = k01 ? o00 + (unsigned)(FETCH_CH * 4) : 0u;
+      dd.o[2] = k10 ? o00 + (unsigned)w * (unsigned)(FETCH_CH * 4) : 0u;
+      dd.o[3] = k11 ? o00 + (unsigned)(w + 1) * (unsigned)(FETCH_CH * 4) : 0u;
+      dd.w[0] = k00 ? tp.nw : 0.f;
+      dd.w[1] = k01 ? tp.ne : 0.f;
+      dd.w[2] = k10 ? tp.sw : 0.f;
+      dd.w[3] = k11 ? tp.se : 0.f;
+      desc[t] = dd;
+    }
+    // normalised xyz of the 5 hypothesis points (model.py:46-48,193): lane m computes point m
+    if (lane < PMVS_NUM_HYP) {
+      float wx, wy, wz;
+      world_point(lane, wx, wy, wz);
+      xyzs[lane * 3 + 0] = __fdiv_rn(__fsub_rn(wx, cam[CB_MEAN + 0]), cam[CB_STD + 0]);
+      xyzs[lane * 3 + 1] = __fdiv_rn(__fsub_rn(wy, cam[CB_MEAN + 1]), cam[CB_STD + 1]);
+      xyzs[lane * 3 + 2] = __fdiv_rn(__fsub_rn(wz, cam[CB_MEAN + 2]), cam[CB_STD + 2]);
+    }
+    __syncwarp();
+
+    // ---- phase 2: fetch + variance over views ---------------------------------------------------
+    const int yy = Y / r, ii = Y - yy * r, xx = X / r, jj = X - xx * r;
+    const int cloud = (ii * r + jj) * p.B + b;
+    float* frow0 = p.feature + ((size_t)cloud * Npts + (size_t)yy * wsub + xx) * PMVS_FEAT_CH;  // hypothesis 0
+    if (lane < FETCH_C4) {
+#pragma unroll 1
+      for (int m = 0; m < PMVS_NUM_HYP; ++m) {
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+        const char* vb = src0;
+#pragma unroll 2
+        for (int v = 0; v < V; ++v, vb += vstride) {
+          const Desc dd = desc[m * V + v];
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(vb + dd.o[0]));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(vb + dd.o[1]));
+          const float4 t2 = __ldg(reinterpret_cast<const float4*>(vb + dd.o[2]));
+          const float4 t3 = __ldg(reinterpret_cast<const float4*>(vb + dd.o[3]));
+          // ATen grid_sampler_2d accumulation order: NW, NE, SW, SE
+          float4 acc;
+          acc.x = fmaf(t3.x, dd.w[3], fmaf(t2.x, dd.w[2], fmaf(t1.x, dd.w[1], __fmul_rn(t0.x, dd.w[0]))));
+          acc.y = fmaf(t3.y, dd.w[3], fmaf(t2.y, dd.w[2], fmaf(t1.y, dd.w[1], __fmul_rn(t0.y, dd.w[0]))));
+          acc.z = fmaf(t3.z, dd.w[3], fmaf(t2.z, dd.w[2], fmaf(t1.z, dd.w[1], __fmul_rn(t0.z, dd.w[0]))));
+          acc.w = fmaf(t3.w, dd.w[3], fmaf(t2.w, dd.w[2], fmaf(t1.w, dd.w[1], __fmul_rn(t0.w, dd.w[0]))));
+          // model.py:188-189: sums over views of x and x**2, in view order
+          s1.x = __fadd_rn(s1.x, acc.x); s1.y = __fadd_rn(s1.y, acc.y);
+          s1.z = __fadd_rn(s1.z, acc.z); s1.w = __fadd_rn(s1.w, acc.w);
+          s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
+          s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
         }
-        dd.nx = nx; dd.ny = ny; dd.pad0 = 0; dd.pad1 = 0;
-        desc[t * 3 + l] = dd;
+        // model.py:190: mean(x^2) - mean(x)^2 (difference unfused); mean = sum * (1/V) as ATen's
+        // CUDA mean kernel computes it (identical to sum / V for V a power of two)
+        float4 o;
+        float a;
+        a = __fmul_rn(s1.x, rV); o.x = __fsub_rn(__fmul_rn(s2.x, rV), __fmul_rn(a, a));
+        a = __fmul_rn(s1.y, rV); o.y = __fsub_rn(__fmul_rn(s2.y, rV), __fmul_rn(a, a));
+        a = __fmul_rn(s1.z, rV); o.z = __fsub_rn(__fmul_rn(s2.z, rV), __fmul_rn(a, a));
+        a = __fmul_rn(s1.w, rV); o.w = __fsub_rn(__fmul_rn(s2.w, rV), __fmul_rn(a, a));
+        st4(frow0 + m * fstep + lane * 4, o);
+      }
+    } else {
+      // lanes 28..31: normalised xyz, tiled 8x into channels 112..135 (model.py:193-197) and kept
+      // planar for the kNN
+      const int q = lane - FETCH_C4;  // 0..3
+#pragma unroll
+      for (int m = 0; m < PMVS_NUM_HYP; ++m) {
+        const float nx = xyzs[m * 3 + 0], ny = xyzs[m * 3 + 1], nz = xyzs[m * 3 + 2];
+        // float4 #j of the 24 tiled values starts at component (4j) % 3 = j % 3
+        for (int j = q; j < 6; j += 4) {
+          const int ph = j % 3;
+          float4 o;
+          o.x = ph == 0 ? nx : (ph == 1 ? ny : nz);
+          o.y = ph == 0 ? ny : (ph == 1 ? nz : nx);
+          o.z = ph == 0 ? nz : (ph == 1 ? nx : ny);
+          o.w = o.x;
+          st4(frow0 + m * fstep + 112 + j * 4, o);
+        }
+        if (q < 3) {
+          const int n = (m * hs + yy) * wsub + xx;
+          p.xyz[((size_t)cloud * 3 + q) * Npts + n] = q == 0 ? nx : (q == 1 ? ny : nz);
+        }
       }
     }
-  }
-  // normalised xyz of the 5 hypothesis points (model.py:46-48,193): lane m computes point m
-  float* xyzs = reinterpret_cast<float*>(dyn_smem + fetch_smem_bytes(V)) + warp * 16;
-  if (lane < PMVS_NUM_HYP) {
-    float wx, wy, wz;
-    world_point(lane, wx, wy, wz);
-    xyzs[lane * 3 + 0] = __fdiv_rn(__fsub_rn(wx, cam[CB_MEAN + 0]), cam[CB_STD + 0]);
-    xyzs[lane * 3 + 1] = __fdiv_rn(__fsub_rn(wy, cam[CB_MEAN + 1]), cam[CB_STD + 1]);
-    xyzs[lane * 3 + 2] = __fdiv_rn(__fsub_rn(wz, cam[CB_MEAN + 2]), cam[CB_STD + 2]);
-  }
-  __syncwarp();
-
-  // ---- phase 2: one pyramid level at a time, all 32 lanes on that level ----------------------
-  // (see level_pass: hypotheses side by side in lane groups, views sequentially)
-  const int r = p.ratio;
-  const int hs = h / r, wsub = w / r;
-  const int yy = Y / r, ii = Y - yy * r, xx = X / r, jj = X - xx * r;
-  const int cloud = (ii * r + jj) * p.B + b;
-  const int Npts = PMVS_NUM_HYP * hs * wsub;
-  const float rV = __frcp_rn((float)V);
-  float* frow0 = p.feature + ((size_t)cloud * Npts + (size_t)yy * wsub + xx) * PMVS_FEAT_CH;  // hypothesis 0
-  const size_t fstep = (size_t)hs * wsub * PMVS_FEAT_CH;                                       // next hypothesis
-
-  level_pass<2>(p, desc, b, V, lane, rV, frow0, fstep);
-  level_pass<1>(p, desc, b, V, lane, rV, frow0, fstep);
-  level_pass<0>(p, desc, b, V, lane, rV, frow0, fstep);
-
-  // normalised xyz: tiled 8x into channels 112..135 (model.py:193-197) and kept planar for the kNN
-#pragma unroll
-  for (int m = 0; m < PMVS_NUM_HYP; ++m) {
-    const float nx = xyzs[m * 3 + 0], ny = xyzs[m * 3 + 1], nz = xyzs[m * 3 + 2];
-    if (lane < 6) {
-      const int ph = lane % 3;  // float4 #q starts at component (4q) % 3 = q % 3
-      float4 o;
-      o.x = ph == 0 ? nx : (ph == 1 ? ny : nz);
-      o.y = ph == 0 ? ny : (ph == 1 ? nz : nx);
-      o.z = ph == 0 ? nz : (ph == 1 ? nx : ny);
-      o.w = o.x;
-      st4(frow0 + m * fstep + 112 + lane * 4, o);
-    } else if (lane < 9) {
-      const int comp = lane - 6;
-      const int n = (m * hs + yy) * wsub + xx;
-      p.xyz[((size_t)cloud * 3 + comp) * Npts + n] = comp == 0 ? nx : (comp == 1 ? ny : nz);
-    }
+    __syncwarp();  // descriptors / xyz are rewritten for the next pixel
   }
 }
 
@@ -576,19 +541,30 @@ int launch_cam_setup(const float* cam_params, const float* interval, const float
   return check_launch("cam_setup_kernel", st);
 }
 
-int launch_fused_fetch(const FusedFetchParams& p, cudaStream_t st) {
-  dim3 grid(cdiv((long long)p.h * p.w, FETCH_WARPS), p.B);
+int launch_warp_source(const float* const pyr[3], const int hl[3], const int wl[3], float* out, int BV, int h, int w,
+                       cudaStream_t st) {
+  WarpSourceParams q{};
+  for (int l = 0; l < 3; ++l) { q.pyr[l] = pyr[l]; q.hl[l] = hl[l]; q.wl[l] = wl[l]; }
+  q.out = out; q.h = h; q.w = w;
+  q.total = (long long)BV * h * w * FETCH_C4;
+  PMVS_REQUIRE(q.total > 0 && cdiv(q.total, 256) < (1ll << 31), "warp_source: bad shape");
+  prof_begin("warp_source", st);
+  warp_source_kernel<<<(unsigned)cdiv(q.total, 256), 256, 0, st>>>(q);
+  return check_launch("warp_source_kernel", st);
+}
+
+size_t warp_source_bytes(int B, int V, int h, int w) { return (size_t)B * V * h * w * FETCH_CH * sizeof(float); }
+
+int launch_fused_fetch(const FusedFetchParams& p0, cudaStream_t st) {
+  FusedFetchParams p = p0;
+  const long long npix = (long long)p.h * p.w;
+  // tap offsets are 32-bit byte offsets inside one view's [h, w, 112] map
+  PMVS_REQUIRE(npix * FETCH_CH * 4 < (1ll << 32), "fused_fetch: flow grid %dx%d too large", p.h, p.w);
+  // several consecutive pixels per warp once there are enough pixels to fill the machine
+  const long long per = npix / (148ll * FETCH_WARPS * 8);
+  p.ppw = per >= 4 ? 4 : (per >= 2 ? 2 : 1);
+  dim3 grid(cdiv(npix, FETCH_WARPS * p.ppw), p.B);
   const size_t smem = fetch_smem_total(p.V);
-  static size_t smem_set = 0;  // per-process high-water mark of the opt-in dynamic smem size
-  if (smem > 40 * 1024 && smem > smem_set) {  // static smem (camera block) counts against the 48 KB default
-    if (cudaFuncSetAttribute(fused_fetch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess) {
-      cudaGetLastError();
-      set_error("fused_fetch: cannot reserve %zu bytes of shared memory (V=%d)", smem, p.V);
-      return PMVS_ERR_CUDA;
-    }
-    smem_set = smem;
-  }
   prof_begin("fused_fetch", st);
   fused_fetch_kernel<<<grid, FETCH_WARPS * 32, smem, st>>>(p);
   return check_launch("fused_fetch_kernel", st);

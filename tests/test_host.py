@@ -49,7 +49,7 @@ def test_workspace_plan_sizes():
     need = _lib.lib.pmvs_point_flow_workspace_bytes(C.byref(s))
     rows = 16 * 25600
     assert need >= rows * (136 + 3 + 16 + 128 + 224 + 64 + 64 + 16) * 4
-    assert need < rows * 700 * 4
+    assert need < rows * 800 * 4  # includes the [B,V,h,w,112] warp source map (model.py:184)
     off = (C.c_size_t * 8)()
     assert _lib.lib.pmvs_point_flow_debug_offsets(C.byref(s), C.byref(off)) == 0
     assert all(o % 256 == 0 for o in off)
