@@ -115,7 +115,7 @@ struct FusedFetchParams {
   float* feature;           // [S,B,N,136]
   float* xyz;               // [S,B,3,N]
   int B, V, h, w, hp, wp, ratio;
-  int ppw;                  // pixels per warp (set by the launcher)
+  int ppw, hs, ws, rlog2;   // set by the launcher: pixels per warp, sub-grid size, log2(ratio) or -1
 };
 // model.py:184 for the three levels at once: channels-last pyramids [B*V,hl,wl,16<<l] -> [B*V,h,w,112]
 int launch_warp_source(const float* const pyr[3], const int hl[3], const int wl[3], float* out, int BV, int h, int w,

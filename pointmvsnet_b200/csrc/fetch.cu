@@ -98,7 +98,7 @@ __device__ __forceinline__ float dot3(const float* r, float x, float y, float z)
 __device__ __forceinline__ float grid_coord(float u, int size) {
   const float sm1 = (float)(size - 1);
   const float g = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(u, 0.5f), sm1), 2.f), 1.f);
-  return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), sm1);
+  return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), sm1);  // x / 2 == x * 0.5 exactly
 }
 
 __device__ __forceinline__ void project(const float* R, const float* t, const float* K, float wx, float wy, float wz,
@@ -211,27 +211,26 @@ constexpr int FETCH_C4 = FETCH_CH / 4;
 struct WarpSourceParams {
   const float* pyr[3];  // channels-last [B*V, hl, wl, 16 << l]
   int hl[3], wl[3];
+  float sy[3], sx[3];   // hl / h, wl / w
   float* out;           // [B*V, h, w, 112]
   int h, w;
-  long long total;      // float4 elements
 };
 
 __global__ void __launch_bounds__(256) warp_source_kernel(const WarpSourceParams p) {
-  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (e >= p.total) return;
-  const int c4 = (int)(e % FETCH_C4);
-  long long t = e / FETCH_C4;
-  const int x = (int)(t % p.w);
-  t /= p.w;
-  const int y = (int)(t % p.h);
-  const long long bv = t / p.h;
+  // grid: x = chunks of 256 float4s along one output row (w * 28 float4s), y = output row, z = b*V + v
+  const int xi = blockIdx.x * 256 + threadIdx.x;
+  if (xi >= p.w * FETCH_C4) return;
+  const int x = xi / FETCH_C4, c4 = xi - x * FETCH_C4;
+  const int y = blockIdx.y;
+  const long long bv = blockIdx.z;
   const int l = c4 < 4 ? 0 : (c4 < 12 ? 1 : 2);
   const int cq = c4 - (l == 0 ? 0 : (l == 1 ? 4 : 12));
   const int C4 = 4 << l;
   const int hi = l == 0 ? p.hl[0] : (l == 1 ? p.hl[1] : p.hl[2]);  // (no dynamic indexing of the parameter struct)
   const int wi = l == 0 ? p.wl[0] : (l == 1 ? p.wl[1] : p.wl[2]);
   const float* lvl = l == 0 ? p.pyr[0] : (l == 1 ? p.pyr[1] : p.pyr[2]);
-  const float sy = (float)hi / (float)p.h, sx = (float)wi / (float)p.w;  // area_pixel_compute_scale
+  const float sy = l == 0 ? p.sy[0] : (l == 1 ? p.sy[1] : p.sy[2]);  // area_pixel_compute_scale: in / out
+  const float sx = l == 0 ? p.sx[0] : (l == 1 ? p.sx[1] : p.sx[2]);
   float fy = __fsub_rn(__fmul_rn(sy, (float)y + 0.5f), 0.5f), fx = __fsub_rn(__fmul_rn(sx, (float)x + 0.5f), 0.5f);
   fy = fy < 0.f ? 0.f : fy;
   fx = fx < 0.f ? 0.f : fx;
@@ -241,9 +240,10 @@ __global__ void __launch_bounds__(256) warp_source_kernel(const WarpSourceParams
   const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
   const float ly1 = __fsub_rn(fy, (float)y0), ly0 = __fsub_rn(1.f, ly1);
   const float lx1 = __fsub_rn(fx, (float)x0), lx0 = __fsub_rn(1.f, lx1);
-  const float* base = lvl + bv * (long long)hi * wi * C4 * 4 + cq * 4;
-  const float4 v00 = ldg4(base + ((long long)y0 * wi + x0) * C4 * 4), v01 = ldg4(base + ((long long)y0 * wi + x1) * C4 * 4);
-  const float4 v10 = ldg4(base + ((long long)y1 * wi + x0) * C4 * 4), v11 = ldg4(base + ((long long)y1 * wi + x1) * C4 * 4);
+  const float* base = lvl + (bv * hi * wi * C4 + cq) * 4;
+  const int r0 = y0 * wi, r1 = y1 * wi;  // < 2^31 texels per level map (checked by the launcher)
+  const float4 v00 = ldg4(base + (size_t)(r0 + x0) * (C4 * 4)), v01 = ldg4(base + (size_t)(r0 + x1) * (C4 * 4));
+  const float4 v10 = ldg4(base + (size_t)(r1 + x0) * (C4 * 4)), v11 = ldg4(base + (size_t)(r1 + x1) * (C4 * 4));
   float4 o;  // h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11), ATen's association
   o.x = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.x), __fmul_rn(lx1, v01.x))),
                   __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.x), __fmul_rn(lx1, v11.x))));
@@ -253,14 +253,15 @@ __global__ void __launch_bounds__(256) warp_source_kernel(const WarpSourceParams
                   __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.z), __fmul_rn(lx1, v11.z))));
   o.w = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.w), __fmul_rn(lx1, v01.w))),
                   __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.w), __fmul_rn(lx1, v11.w))));
-  st4(p.out + e * 4, o);
+  st4(p.out + ((bv * p.h + y) * (long long)p.w * FETCH_C4 + xi) * 4, o);
 }
 
 constexpr int FETCH_WARPS = 8;
 
-// Sampling descriptor of one (hypothesis, view): byte offsets of the NW, NE, SW, SE texels inside
-// the view's [h, w, 112] map and their grid_sample weights.  Out-of-range taps (zeros padding)
-// carry weight 0 and offset 0, so the consumer runs 4 unconditional taps: fma(t, 0, acc) == acc.
+// Sampling descriptor of one (hypothesis, view): offsets, in float4 units from the start of the
+// batch element's [V, h, w, 112] map, of the NW, NE, SW, SE texels and their grid_sample weights.
+// Out-of-range taps (zeros padding) carry weight 0 and a valid offset, so the consumer runs 4
+// unconditional taps: fma(t, 0, acc) == acc.
 struct __align__(16) Desc {
   unsigned o[4];
   float w[4];
@@ -274,18 +275,18 @@ __host__ __device__ constexpr size_t fetch_smem_total(int V) {  // + 16 floats o
   return fetch_smem_bytes(V) + FETCH_WARPS * 16 * sizeof(float);
 }
 
-// rows a2-a9 for p.ppw consecutive pixels per warp.  Phase 1: lane t = (hypothesis m, view v)
-// un-projects the hypothesis, projects it into the view and writes the 4-tap descriptor.  Phase 2:
-// lanes 0..27 each own one float4 of the 112 channels; for every hypothesis the views are walked in
-// order and the lane keeps the sum / sum of squares of its channels (model.py:188-189), so there
-// is no cross-lane reduction; one tap = one 128-bit ld.global.nc + 4 FFMA per lane, 448 contiguous
-// bytes per warp.
-__global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const FusedFetchParams p) {
+// rows a2-a9; a CTA covers (4 * p.ppw) x 2 pixels, one pixel per warp at a time.  Phase 1: lane t =
+// (hypothesis m, view v) un-projects the hypothesis, projects it into the view and writes the
+// 4-tap descriptor.  Phase 2: lanes 0..27 each own one float4 of the 112 channels; for every
+// hypothesis the views are walked in order and the lane keeps the sum / sum of squares of its
+// channels (model.py:188-189), so there is no cross-lane reduction; one tap = one 128-bit
+// ld.global.nc + 4 FFMA per lane, 448 contiguous bytes per warp.
+__global__ void __launch_bounds__(FETCH_WARPS * 32, 4) fused_fetch_kernel(const FusedFetchParams p) {
   __shared__ __align__(16) float cam[cam_block_floats(PMVS_MAX_VIEWS)];
   __shared__ __align__(8) unsigned long long bar;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
 
-  const int b = blockIdx.y;
+  const int b = blockIdx.z;
   const int V = p.V;
   // --- stage this batch element's camera block: one TMA bulk copy + mbarrier ------------
   const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&bar);
@@ -324,28 +325,40 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
   float* xyzs = reinterpret_cast<float*>(dyn_smem + fetch_smem_bytes(V)) + warp * 16;
   const float interval = cam[CB_INTERVAL];
   const float nsy = (float)p.hp / (float)h, nsx = (float)p.wp / (float)w;
-  const int r = p.ratio;
-  const int hs = h / r, wsub = w / r;
+  const int hs = p.hs, wsub = p.ws;
   const int Npts = PMVS_NUM_HYP * hs * wsub;
   const float rV = __frcp_rn((float)V);
   const size_t fstep = (size_t)hs * wsub * PMVS_FEAT_CH;  // next hypothesis
-  const size_t vstride = (size_t)h * w * FETCH_CH * sizeof(float);
-  const char* src0 = reinterpret_cast<const char*>(p.src) + (size_t)b * V * vstride + lane * 16;
+  const float4* src = reinterpret_cast<const float4*>(p.src) + (size_t)b * V * h * w * FETCH_C4 + lane;
+  // (hypothesis, view) pairs this lane describes: t = lane and, for V > 6, lane + 32
+  const int m_a = lane / V, v_a = lane - m_a * V;
+  const int m_b = (lane + 32) / V, v_b = lane + 32 - m_b * V;
+  // lane -> (hypothesis, float4 #j of the 24 tiled xyz values) and (hypothesis, component) for the
+  // epilogue stores; float4 #j starts at component (4j) % 3 = j % 3
+  const int em = lane / 6, ej = lane - em * 6, eph = ej % 3;
+  const int e0 = em * 3 + eph, e1 = em * 3 + (eph + 1) % 3, e2 = em * 3 + (eph + 2) % 3;
 
-  const int pix0 = (blockIdx.x * FETCH_WARPS + warp) * p.ppw;
+  // At step k the 8 warps of the CTA cover a 4 x 2 block of ADJACENT pixels, so the taps they have
+  // in flight overlap in L1 (neighbouring pixels project about one texel apart).
+  const int Y = blockIdx.y * 2 + (warp >> 2);
+  if (Y >= h) return;  // warp-uniform; no CTA-wide barrier below
+  const int yy = p.rlog2 >= 0 ? Y >> p.rlog2 : Y / p.ratio;
+  const int ii = Y - yy * p.ratio;
+  int ys = (int)floorf((float)Y * nsy);  // nearest upsample row (model.py:153-158; ATen nearest rule)
+  ys = ys < p.hp - 1 ? ys : p.hp - 1;
+  const float py = (float)Y + 0.5f;
+  const int X0 = blockIdx.x * p.ppw * 4 + (warp & 3);
+
   for (int k = 0; k < p.ppw; ++k) {
-    const int pix = pix0 + k;
-    if (pix >= h * w) break;  // warp-uniform
-    const int Y = pix / w, X = pix - Y * w;
+    const int X = X0 + k * 4;
+    if (X >= w) break;  // warp-uniform
 
-    // nearest upsample of the previous depth (model.py:153-158; ATen nearest index rule)
-    int ys = (int)floorf((float)Y * nsy), xs = (int)floorf((float)X * nsx);
-    ys = ys < p.hp - 1 ? ys : p.hp - 1;
+    int xs = (int)floorf((float)X * nsx);
     xs = xs < p.wp - 1 ? xs : p.wp - 1;
     const float dprev = __ldg(p.depth_prev + ((size_t)b * p.hp + ys) * p.wp + xs);
 
     // uv = K_ref^-1 * (x + .5, y + .5, 1)   (functions.py:128-138, model.py:165-170)
-    const float px = (float)X + 0.5f, py = (float)Y + 0.5f;
+    const float px = (float)X + 0.5f;
     const float uvx = dot3(cam + CB_KINV + 0, px, py, 1.f);
     const float uvy = dot3(cam + CB_KINV + 3, px, py, 1.f);
     const float uvz = dot3(cam + CB_KINV + 6, px, py, 1.f);
@@ -362,7 +375,7 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
 
     // ---- phase 1: one lane per (hypothesis, view) builds its sampling descriptor --------------
     for (int t = lane; t < npair; t += 32) {
-      const int m = t / V, v = t - m * V;
+      const int m = t < 32 ? m_a : m_b, v = t < 32 ? v_a : v_b;
       float wx, wy, wz;
       world_point(m, wx, wy, wz);
       const float* cv = cam + CB_VIEW + v * CB_VSTRIDE;
@@ -372,12 +385,13 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
       const bool ok = usable(ix) && usable(iy);
       const Taps tp = make_taps(ok ? ix : -10.f, ok ? iy : -10.f, w, h);
       const bool k00 = tp.ok_n && tp.ok_w, k01 = tp.ok_n && tp.ok_e, k10 = tp.ok_s && tp.ok_w, k11 = tp.ok_s && tp.ok_e;
-      const unsigned o00 = (unsigned)(tp.y0 * w + tp.x0) * (unsigned)(FETCH_CH * 4);
+      const unsigned ov = (unsigned)(v * h * w) * (unsigned)FETCH_C4;  // start of the view
+      const unsigned o00 = ov + (unsigned)(tp.y0 * w + tp.x0) * (unsigned)FETCH_C4;
       Desc dd;
-      dd.o[0] = k00 ? o00 : 0u;
-      dd.o[1] = k01 ? o00 + (unsigned)(FETCH_CH * 4) : 0u;
-      dd.o[2] = k10 ? o00 + (unsigned)w * (unsigned)(FETCH_CH * 4) : 0u;
-      dd.o[3] = k11 ? o00 + (unsigned)(w + 1) * (unsigned)(FETCH_CH * 4) : 0u;
+      dd.o[0] = k00 ? o00 : ov;
+      dd.o[1] = k01 ? o00 + (unsigned)FETCH_C4 : ov;
+      dd.o[2] = k10 ? o00 + (unsigned)w * (unsigned)FETCH_C4 : ov;
+      dd.o[3] = k11 ? o00 + (unsigned)(w + 1) * (unsigned)FETCH_C4 : ov;
       dd.w[0] = k00 ? tp.nw : 0.f;
       dd.w[1] = k01 ? tp.ne : 0.f;
       dd.w[2] = k10 ? tp.sw : 0.f;
@@ -395,21 +409,22 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
     __syncwarp();
 
     // ---- phase 2: fetch + variance over views ---------------------------------------------------
-    const int yy = Y / r, ii = Y - yy * r, xx = X / r, jj = X - xx * r;
-    const int cloud = (ii * r + jj) * p.B + b;
+    const int xx = p.rlog2 >= 0 ? X >> p.rlog2 : X / p.ratio;
+    const int jj = X - xx * p.ratio;
+    const int cloud = (ii * p.ratio + jj) * p.B + b;
     float* frow0 = p.feature + ((size_t)cloud * Npts + (size_t)yy * wsub + xx) * PMVS_FEAT_CH;  // hypothesis 0
     if (lane < FETCH_C4) {
+      const Desc* dp = desc;
 #pragma unroll 1
       for (int m = 0; m < PMVS_NUM_HYP; ++m) {
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-        const char* vb = src0;
 #pragma unroll 2
-        for (int v = 0; v < V; ++v, vb += vstride) {
-          const Desc dd = desc[m * V + v];
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(vb + dd.o[0]));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(vb + dd.o[1]));
-          const float4 t2 = __ldg(reinterpret_cast<const float4*>(vb + dd.o[2]));
-          const float4 t3 = __ldg(reinterpret_cast<const float4*>(vb + dd.o[3]));
+        for (int v = 0; v < V; ++v, ++dp) {
+          const Desc dd = *dp;
+          const float4 t0 = __ldg(src + dd.o[0]);
+          const float4 t1 = __ldg(src + dd.o[1]);
+          const float4 t2 = __ldg(src + dd.o[2]);
+          const float4 t3 = __ldg(src + dd.o[3]);
           // ATen grid_sampler_2d accumulation order: NW, NE, SW, SE
           float4 acc;
           acc.x = fmaf(t3.x, dd.w[3], fmaf(t2.x, dd.w[2], fmaf(t1.x, dd.w[1], __fmul_rn(t0.x, dd.w[0]))));
@@ -432,28 +447,16 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32) fused_fetch_kernel(const Fus
         a = __fmul_rn(s1.w, rV); o.w = __fsub_rn(__fmul_rn(s2.w, rV), __fmul_rn(a, a));
         st4(frow0 + m * fstep + lane * 4, o);
       }
-    } else {
-      // lanes 28..31: normalised xyz, tiled 8x into channels 112..135 (model.py:193-197) and kept
-      // planar for the kNN
-      const int q = lane - FETCH_C4;  // 0..3
-#pragma unroll
-      for (int m = 0; m < PMVS_NUM_HYP; ++m) {
-        const float nx = xyzs[m * 3 + 0], ny = xyzs[m * 3 + 1], nz = xyzs[m * 3 + 2];
-        // float4 #j of the 24 tiled values starts at component (4j) % 3 = j % 3
-        for (int j = q; j < 6; j += 4) {
-          const int ph = j % 3;
-          float4 o;
-          o.x = ph == 0 ? nx : (ph == 1 ? ny : nz);
-          o.y = ph == 0 ? ny : (ph == 1 ? nz : nx);
-          o.z = ph == 0 ? nz : (ph == 1 ? nx : ny);
-          o.w = o.x;
-          st4(frow0 + m * fstep + 112 + j * 4, o);
-        }
-        if (q < 3) {
-          const int n = (m * hs + yy) * wsub + xx;
-          p.xyz[((size_t)cloud * 3 + q) * Npts + n] = q == 0 ? nx : (q == 1 ? ny : nz);
-        }
-      }
+    }
+    // normalised xyz: tiled 8x into channels 112..135 (model.py:193-197), 5 x 6 float4s = lanes 0..29,
+    // and kept planar for the kNN (5 x 3 floats = lanes 0..14)
+    if (lane < PMVS_NUM_HYP * 6) {
+      const float4 o = make_float4(xyzs[e0], xyzs[e1], xyzs[e2], xyzs[e0]);
+      st4(frow0 + em * fstep + 112 + ej * 4, o);
+    }
+    if (lane < PMVS_NUM_HYP * 3) {
+      const int m = lane / 3, comp = lane - m * 3;
+      p.xyz[((size_t)cloud * 3 + comp) * Npts + (m * hs + yy) * wsub + xx] = xyzs[lane];
     }
     __syncwarp();  // descriptors / xyz are rewritten for the next pixel
   }
@@ -546,10 +549,14 @@ int launch_warp_source(const float* const pyr[3], const int hl[3], const int wl[
   WarpSourceParams q{};
   for (int l = 0; l < 3; ++l) { q.pyr[l] = pyr[l]; q.hl[l] = hl[l]; q.wl[l] = wl[l]; }
   q.out = out; q.h = h; q.w = w;
-  q.total = (long long)BV * h * w * FETCH_C4;
-  PMVS_REQUIRE(q.total > 0 && cdiv(q.total, 256) < (1ll << 31), "warp_source: bad shape");
+  PMVS_REQUIRE(BV > 0 && BV <= 65535 && h > 0 && h <= 65535 && w > 0, "warp_source: bad shape");
+  for (int l = 0; l < 3; ++l) {
+    PMVS_REQUIRE((long long)hl[l] * wl[l] < (1ll << 31), "warp_source: level %d too large", l);
+    q.sy[l] = (float)hl[l] / (float)h; q.sx[l] = (float)wl[l] / (float)w;
+  }
+  dim3 grid(cdiv((long long)w * FETCH_C4, 256), h, BV);
   prof_begin("warp_source", st);
-  warp_source_kernel<<<(unsigned)cdiv(q.total, 256), 256, 0, st>>>(q);
+  warp_source_kernel<<<grid, 256, 0, st>>>(q);
   return check_launch("warp_source_kernel", st);
 }
 
@@ -558,12 +565,16 @@ size_t warp_source_bytes(int B, int V, int h, int w) { return (size_t)B * V * h 
 int launch_fused_fetch(const FusedFetchParams& p0, cudaStream_t st) {
   FusedFetchParams p = p0;
   const long long npix = (long long)p.h * p.w;
-  // tap offsets are 32-bit byte offsets inside one view's [h, w, 112] map
-  PMVS_REQUIRE(npix * FETCH_CH * 4 < (1ll << 32), "fused_fetch: flow grid %dx%d too large", p.h, p.w);
-  // several consecutive pixels per warp once there are enough pixels to fill the machine
+  // tap offsets are 32-bit float4 offsets inside one batch element's [V, h, w, 112] map
+  PMVS_REQUIRE(npix * p.V * FETCH_C4 < (1ll << 32), "fused_fetch: V=%d x %dx%d too large", p.V, p.h, p.w);
+  PMVS_REQUIRE(p.h <= 65535 && p.B <= 65535, "fused_fetch: h or B too large");
+  p.hs = p.h / p.ratio; p.ws = p.w / p.ratio;
+  p.rlog2 = -1;
+  for (int q = 0; q < 16; ++q) if ((1 << q) == p.ratio) p.rlog2 = q;
+  // several consecutive pixels of a row per warp once there are enough pixels to fill the machine
   const long long per = npix / (148ll * FETCH_WARPS * 8);
   p.ppw = per >= 4 ? 4 : (per >= 2 ? 2 : 1);
-  dim3 grid(cdiv(npix, FETCH_WARPS * p.ppw), p.B);
+  dim3 grid(cdiv(p.w, 4 * p.ppw), cdiv(p.h, 2), p.B);  // CTA = (4 * ppw) x 2 pixels
   const size_t smem = fetch_smem_total(p.V);
   prof_begin("fused_fetch", st);
   fused_fetch_kernel<<<grid, FETCH_WARPS * 32, smem, st>>>(p);
