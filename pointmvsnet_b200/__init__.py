@@ -7,6 +7,7 @@ Mirrors the reference's import surface (pointmvsnet/model.py:8-12):
     pointmvsnet_b200.utils.feature_fetcher FeatureFetcher
     pointmvsnet_b200.utils.torch_utils   get_knn_3d
     pointmvsnet_b200.nn.mlp / nn.conv    SharedMLP, Conv1d
+    pointmvsnet_b200.utils.io / utils.eval_file_logger   PFM / camera files, per-view outputs (test.py:76)
 plus the new ``PointFlow`` module that replaces the ``point_flow`` closure
 (pointmvsnet/model.py:150-295).  ``install_as_pointmvsnet()`` aliases these modules
 under the reference's own names so an unchanged ``pointmvsnet/model.py`` imports them.
@@ -31,6 +32,9 @@ def install_as_pointmvsnet(reference_root=None):
         "pointmvsnet.functions.gather_knn": "pointmvsnet_b200.functions.gather_knn",
         "pointmvsnet.utils.feature_fetcher": "pointmvsnet_b200.utils.feature_fetcher",
         "pointmvsnet.utils.torch_utils": "pointmvsnet_b200.utils.torch_utils",
+        # output side (the reference's versions use np.int / ndarray.tostring, gone from numpy 2)
+        "pointmvsnet.utils.io": "pointmvsnet_b200.utils.io",
+        "pointmvsnet.utils.eval_file_logger": "pointmvsnet_b200.utils.eval_file_logger",
     }
     extra = {
         "pointmvsnet.functions.functions": "pointmvsnet_b200.functions.functions",
@@ -43,8 +47,11 @@ def install_as_pointmvsnet(reference_root=None):
         if reference_root not in sys.path:
             sys.path.insert(0, reference_root)
         import pointmvsnet.functions as pf  # the reference package itself
+        import pointmvsnet.utils  # noqa: F401
         for ref_name, ours in hot.items():
             sys.modules[ref_name] = importlib.import_module(ours)
+            parent, _, leaf = ref_name.rpartition(".")
+            setattr(sys.modules[parent], leaf, sys.modules[ref_name])
         pf.dgcnn_ext = sys.modules["pointmvsnet.functions.dgcnn_ext"]
         import pointmvsnet.networks as ref_networks
         from pointmvsnet_b200 import networks as ours_networks
