@@ -71,7 +71,6 @@ __device__ __forceinline__ float bn_apply(float x, float mean, float invstd, flo
 int launch_knn3d(const float* xyz, int64_t* idx64, int32_t* idx32, int clouds, int D, int H, int W,
                  int ksize, int knn, cudaStream_t st);
 int launch_transpose(const float* in, float* out, int batch, int R, int C, cudaStream_t st);
-int launch_resize_cl(const float* in, float* out, int BV, int C, int hi, int wi, int ho, int wo, cudaStream_t st);
 
 struct GemmArgs {
   const float* x;
