@@ -172,20 +172,31 @@ def cpu_reference_pass(cfg_name, steps, warmup, budget_s=240.0):
             break
     torch.set_num_threads(best[0])
     t_it1 = best[1]
-    sample = "one full pass (%d iterations) of the same workload per step" % len(scales)
-    # a full pass costs roughly 21x iteration 1 (21 sub-clouds of equal size)
-    est = t_it1 * 21 * (steps + warmup)
-    if est > budget_s and len(scales) > 2:
-        scales, inters = scales[:2], inters[:2]
-        sample = "first 2 of 3 iterations of the pass (5 of 21 sub-clouds); the full pass would exceed the time bound"
+    # A pass is 1 + 4 + 16 = 21 sub-cloud calls of equal size (25 600 points at C2), so its cost is
+    # proportional to the sub-clouds processed.  A step is the largest prefix of the pass that keeps
+    # the whole run inside the time bound; the rate is then scaled to the full pass by the
+    # sub-cloud count, so `value` stays the metric of the other arm (iterations of the 3-iteration
+    # pass per second).
+    n_sub = [int(round(sc * 8)) ** 2 for sc in scales]          # sub-clouds per iteration: 1, 4, 16
+    total_sub = sum(n_sub)
+    keep = len(scales)
+    while keep > 1 and t_it1 * sum(n_sub[:keep]) * (steps + warmup) > budget_s:
+        keep -= 1
+    frac = sum(n_sub[:keep]) / float(total_sub)
+    if keep == len(scales):
+        sample = "one full pass (%d iterations) of the same workload per step" % len(scales)
+    else:
+        sample = ("first %d of %d iterations of the pass per step (%d of %d equal-sized sub-clouds); time scaled by "
+                  "%d/%d to the full pass" % (keep, len(scales), sum(n_sub[:keep]), total_sub, total_sub, sum(n_sub[:keep])))
+    run_scales, run_inters = scales[:keep], inters[:keep]
     for _ in range(warmup):
-        one(scales, inters)
+        one(run_scales, run_inters)
     times = []
     for _ in range(steps):
         t0 = time.time()
-        one(scales, inters)
+        one(run_scales, run_inters)
         times.append(time.time() - t0)
-    ms = 1e3 * sum(times) / len(times)
+    ms = 1e3 * sum(times) / len(times) / frac   # per full pass
     value = len(scales) / (ms / 1e3)
     return value, ms, {"cores": best[0], "host_cores": cores, "sample": sample, "kind": "port"}
 
