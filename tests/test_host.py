@@ -120,6 +120,12 @@ def test_install_as_pointmvsnet_aliases():
         assert a is b
         from pointmvsnet.functions import dgcnn_ext  # noqa
         assert hasattr(dgcnn_ext, "gather_knn_forward") and hasattr(dgcnn_ext, "gather_knn_backward")
+        # output side (test.py:19,76; dataset.py:114,122): the reference's module and function names
+        import pointmvsnet.utils.io as ref_io  # noqa
+        from pointmvsnet.utils.eval_file_logger import eval_file_logger  # noqa
+        for fn in ("mkdir", "load_cam_dtu", "write_cam_dtu", "load_pfm", "write_pfm"):
+            assert callable(getattr(ref_io, fn))
+        assert eval_file_logger.__module__ == "pointmvsnet_b200.utils.eval_file_logger"
     finally:
         for k in [k for k in sys.modules if k == "pointmvsnet" or k.startswith("pointmvsnet.")]:
             del sys.modules[k]
