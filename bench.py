@@ -220,6 +220,31 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def per_iteration_kernel_ms(recs, n_iter):
+    """Profile records [(kernel name, ms)] in launch order -> mean kernel-time per iteration size.
+
+    Every iteration of a pass starts with the `cam_setup` launch (csrc/api.cu, pmvs_point_flow_iter);
+    launches before the first one of a pass (the pyramid transposes) are not part of an iteration.
+    Returns a list of n_iter floats (ms, summed kernel time of that iteration averaged over the
+    recorded passes) or None if the records do not have that structure."""
+    sums = [0.0] * n_iter
+    counts = [0] * n_iter
+    it = -1
+    seen = 0
+    for name, ms in recs:
+        if name == "cam_setup":
+            it = seen % n_iter
+            seen += 1
+            counts[it] += 1
+        elif name == "transpose":
+            it = -1
+        if it >= 0:
+            sums[it] += ms
+    if seen == 0 or seen % n_iter != 0 or len(set(counts)) != 1:
+        return None
+    return [s / counts[0] for s in sums]
+
+
 # --------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------
@@ -383,6 +408,7 @@ def run_ours(args):
     roofline = None
     roofline_gemm = None
     kernel_table = None
+    by_size = None
     if rank == 0:
         with torch.no_grad():
             eager = PointFlowPass(pf, IMG_SCALES, INTER_SCALES)
@@ -403,6 +429,15 @@ def run_ours(args):
             a = agg.setdefault(name, [0.0, 0])
             a[0] += ms
             a[1] += 1
+        by_size = None
+        try:  # per-iteration-size rates next to the pass rate (kernel time, one view in flight)
+            it_ms = per_iteration_kernel_ms(recs, n_iter)
+            if it_ms is not None:
+                by_size = [{"flow_hw": [int(H * sc), int(W * sc)], "points": 5 * int(H * sc) * int(W * sc),
+                            "kernel_ms": round(m, 4), "iters_per_s": round(1e3 / m, 1)}
+                           for sc, m in zip(IMG_SCALES, it_ms)]
+        except Exception:
+            by_size = None
         alg = algorithmic_bytes_per_pass(H, W, V)
         peaks = {}
         try:
@@ -483,6 +518,7 @@ def run_ours(args):
             "launches_per_step": int(launches_per_pass * G),
             "clocks": clocks, "roofline": roofline, "roofline_gemm": roofline_gemm, "cpu_baseline": cpu_baseline,
             "kernels": kernel_table,
+            "per_iteration_size": by_size,
         }
         result_line = json.dumps(line)
     else:

@@ -196,6 +196,17 @@ def test_bench_algorithmic_bytes_match_survey():
     assert alg["knn3d"][0] == 537600 * 76
 
 
+def test_bench_per_iteration_grouping():
+    sys.path.insert(0, ROOT)
+    import bench
+    one_iter = [("cam_setup", 0.01), ("warp_source", 0.1), ("fused_fetch", 0.2), ("knn3d", 0.3)]
+    one_pass = [("transpose", 1.0)] * 3 + one_iter + [(n, 2 * m) for n, m in one_iter] + [(n, 4 * m) for n, m in one_iter]
+    ms = bench.per_iteration_kernel_ms(one_pass * 5, 3)
+    assert ms == pytest.approx([0.61, 1.22, 2.44])
+    assert bench.per_iteration_kernel_ms(one_pass[:-4], 3) is None   # truncated pass
+    assert bench.per_iteration_kernel_ms([("knn3d", 1.0)], 3) is None
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/pointmvsnet"), reason="reference checkout not present")
 def test_unchanged_reference_model_imports_our_operators():
     """Drop-in check (build container only): with install_as_pointmvsnet(reference_root) the
