@@ -267,6 +267,30 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
       c0 = make_float4(fmaf(-(m.x + loc.x), A4.x, bt.x), fmaf(-(m.y + loc.y), A4.y, bt.y),
                        fmaf(-(m.z + loc.z), A4.z, bt.z), fmaf(-(m.w + loc.w), A4.w, bt.w));
     }
+#if PMVS_F32X2
+    // same arithmetic on fp32 pairs: apply 2 FFMA2 + 4 FMNMX + 2 FADD2, stats 6 packed ops per float4
+    const f32x2 A_lo = APPLY ? pack2(A4.x, A4.y) : 0ull, A_hi = APPLY ? pack2(A4.z, A4.w) : 0ull;
+    const f32x2 c_lo = APPLY ? pack2(c0.x, c0.y) : 0ull, c_hi = APPLY ? pack2(c0.z, c0.w) : 0ull;
+    const f32x2 l_lo = pack2(loc.x, loc.y), l_hi = pack2(loc.z, loc.w);
+    f32x2 o_lo = pack2(0.f, 0.f), o_hi = o_lo;
+    f32x2 n1_lo = pack2(sn1.x, sn1.y), n1_hi = pack2(sn1.z, sn1.w);
+    f32x2 n2_lo = pack2(sn2.x, sn2.y), n2_hi = pack2(sn2.z, sn2.w);
+    auto body = [&](int nb) {
+      const float4 e = ldg4(a.le + (cloud_base + nb) * LD + COUT + cl);
+      const f32x2 e_lo = pack2(e.x, e.y), e_hi = pack2(e.z, e.w);
+      if (APPLY) {
+        float t0, t1, t2, t3;
+        unpack2(fma2(e_lo, A_lo, c_lo), t0, t1);
+        unpack2(fma2(e_hi, A_hi, c_hi), t2, t3);
+        o_lo = add2(o_lo, pack2(fmaxf(t0, 0.f), fmaxf(t1, 0.f)));
+        o_hi = add2(o_hi, pack2(fmaxf(t2, 0.f), fmaxf(t3, 0.f)));
+      } else {
+        const f32x2 d_lo = sub2(e_lo, l_lo), d_hi = sub2(e_hi, l_hi);
+        n1_lo = add2(n1_lo, d_lo); n1_hi = add2(n1_hi, d_hi);
+        n2_lo = fma2(d_lo, d_lo, n2_lo); n2_hi = fma2(d_hi, d_hi, n2_hi);
+      }
+    };
+#else
     auto body = [&](int nb) {
       const float4 e = ldg4(a.le + (cloud_base + nb) * LD + COUT + cl);
       if (APPLY) {
@@ -282,6 +306,7 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
         sn2.z = fmaf(dz, dz, sn2.z); sn2.w = fmaf(dw, dw, sn2.w);
       }
     };
+#endif
     if constexpr (KT > 0) {
       static_assert(KT % 4 == 0, "KT");
       int nbs[KT];
@@ -295,6 +320,14 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
     } else {
       for (int k = 0; k < K; ++k) body(__ldg(ip + k));
     }
+#if PMVS_F32X2
+    if (APPLY) {
+      unpack2(o_lo, o.x, o.y); unpack2(o_hi, o.z, o.w);
+    } else {
+      unpack2(n1_lo, sn1.x, sn1.y); unpack2(n1_hi, sn1.z, sn1.w);
+      unpack2(n2_lo, sn2.x, sn2.y); unpack2(n2_hi, sn2.z, sn2.w);
+    }
+#endif
     if (APPLY) {
       const float kf = (float)K;
       float* orow = a.out + row * a.ldo;

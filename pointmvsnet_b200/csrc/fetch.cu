@@ -417,6 +417,27 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32, 4) fused_fetch_kernel(const 
       const Desc* dp = desc;
 #pragma unroll 1
       for (int m = 0; m < PMVS_NUM_HYP; ++m) {
+#if PMVS_F32X2
+        // the same operations on fp32 pairs (FMUL2 / FFMA2 / FADD2): 14 instead of 28 per (m, v)
+        f32x2 s1l = pack2(0.f, 0.f), s1h = s1l, s2l = s1l, s2h = s1l;
+#pragma unroll 2
+        for (int v = 0; v < V; ++v, ++dp) {
+          const Desc dd = *dp;
+          const float4 t0 = __ldg(src + dd.o[0]);
+          const float4 t1 = __ldg(src + dd.o[1]);
+          const float4 t2 = __ldg(src + dd.o[2]);
+          const float4 t3 = __ldg(src + dd.o[3]);
+          const f32x2 w0 = pack2(dd.w[0], dd.w[0]), w1 = pack2(dd.w[1], dd.w[1]);
+          const f32x2 w2 = pack2(dd.w[2], dd.w[2]), w3 = pack2(dd.w[3], dd.w[3]);
+          const f32x2 al = fma2(pack2(t3.x, t3.y), w3, fma2(pack2(t2.x, t2.y), w2, fma2(pack2(t1.x, t1.y), w1, mul2(pack2(t0.x, t0.y), w0))));
+          const f32x2 ah = fma2(pack2(t3.z, t3.w), w3, fma2(pack2(t2.z, t2.w), w2, fma2(pack2(t1.z, t1.w), w1, mul2(pack2(t0.z, t0.w), w0))));
+          s1l = add2(s1l, al); s1h = add2(s1h, ah);
+          s2l = add2(s2l, mul2(al, al)); s2h = add2(s2h, mul2(ah, ah));
+        }
+        float4 s1, s2;
+        unpack2(s1l, s1.x, s1.y); unpack2(s1h, s1.z, s1.w);
+        unpack2(s2l, s2.x, s2.y); unpack2(s2h, s2.z, s2.w);
+#else
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
 #pragma unroll 2
         for (int v = 0; v < V; ++v, ++dp) {
@@ -437,6 +458,7 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32, 4) fused_fetch_kernel(const 
           s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
           s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
         }
+#endif
         // model.py:190: mean(x^2) - mean(x)^2 (difference unfused); mean = sum * (1/V) as ATen's
         // CUDA mean kernel computes it (identical to sum / V for V a power of two)
         float4 o;
