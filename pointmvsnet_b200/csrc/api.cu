@@ -127,6 +127,9 @@ struct FlowPlan {
   size_t R;  // rows = S * B * N
   size_t cam, feature, xyz, idx, le, ecat, h0, h1, h2, stats, total;
   size_t warp_src;     // the pyramid levels resized to the flow grid, [B,V,h,w,112]
+#if PMVS_EDGE_TILE
+  size_t cand;         // [R, 16] bytes: kNN candidate ids for the tile EdgeConv kernels
+#endif
   size_t st_ec[3], st_mlp[3];  // offsets (in doubles) inside the stats region
   size_t stats_doubles;
 };
@@ -158,6 +161,9 @@ static int make_plan(const pmvs_flow_shape* s, FlowPlan& p) {
   p.h1 = o; o += align_up(p.R * 64 * 4);
   p.h2 = o; o += align_up(p.R * 16 * 4);
   p.warp_src = o; o += align_up(warp_source_bytes(s->B, s->V, s->flow_h, s->flow_w));
+#if PMVS_EDGE_TILE
+  p.cand = o; o += align_up(p.R * PMVS_KNN);
+#endif
   size_t d = 0;
   const int ec_cout[3] = {32, 32, 64};
   const int mlp_cout[3] = {64, 64, 16};
@@ -354,7 +360,12 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
   f.ratio = shape->ratio;
   PMVS_TRY(launch_fused_fetch(f, st));
 
+#if PMVS_EDGE_TILE
+  unsigned char* cand = (unsigned char*)(ws + p.cand);
+  PMVS_TRY(launch_knn3d_cand(xyz, idx, cand, S * B, PMVS_NUM_HYP, p.hs, p.ws, st));
+#else
   PMVS_TRY(launch_knn3d(xyz, nullptr, idx, S * B, PMVS_NUM_HYP, p.hs, p.ws, PMVS_NUM_HYP, PMVS_KNN, st));
+#endif
 
   // flow_edge_conv (model.py:213-216): EdgeConvNoC(136,32), EdgeConv(32,32), EdgeConv(64,64)
   const int cin[3] = {136, 32, 64}, cout[3] = {32, 32, 64}, in_off[3] = {0, 0, 32}, out_off[3] = {0, 32, 96};
@@ -369,6 +380,9 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
     e.le = le; e.idx = idx; e.stats = stats + p.st_ec[l]; e.gamma = wts->ec_gamma[l]; e.beta = wts->ec_beta[l];
     e.eps = wts->eps; e.concat_central = l > 0; e.out = ecat + out_off[l]; e.ldo = 224; e.groups = S;
     e.rows_per_group = rows_per_group; e.N = p.N; e.K = PMVS_KNN; e.cout = cout[l];
+#if PMVS_EDGE_TILE
+    e.cand = cand; e.gh = p.hs; e.gw = p.ws;
+#endif
     PMVS_TRY(launch_edge_stats(e, st));
     PMVS_TRY(launch_edge_apply(e, st));
   }

@@ -55,6 +55,10 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 #ifndef PMVS_F32X2
 #define PMVS_F32X2 0
 #endif
+// EXPERIMENTAL shared-memory-tile EdgeConv kernels (csrc/edge_tile.cuh), same rule: -DPMVS_EDGE_TILE=1 only
+#ifndef PMVS_EDGE_TILE
+#define PMVS_EDGE_TILE 0
+#endif
 #if PMVS_F32X2
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float a, float b) {
@@ -104,6 +108,11 @@ __device__ __forceinline__ float bn_apply(float x, float mean, float invstd, flo
 }
 
 // ---- internal launchers shared between translation units ---------------------------
+#if PMVS_EDGE_TILE
+// knn3d with the additional 1-byte candidate-id output the tile kernels consume (ksize 5, knn 16, int32)
+int launch_knn3d_cand(const float* xyz, int32_t* idx32, unsigned char* cand, int clouds, int D, int H, int W,
+                      cudaStream_t st);
+#endif
 int launch_knn3d(const float* xyz, int64_t* idx64, int32_t* idx32, int clouds, int D, int H, int W,
                  int ksize, int knn, cudaStream_t st);
 int launch_transpose(const float* in, float* out, int batch, int R, int C, cudaStream_t st);
@@ -139,6 +148,10 @@ struct EdgeArgs {
   float* out;
   int ldo;
   int groups, rows_per_group, N, K, cout;
+#if PMVS_EDGE_TILE
+  const unsigned char* cand;  // [R, 16] kNN candidate ids (255 = out-of-grid pick, use idx); NULL = gather path
+  int gh, gw;                 // sub-grid size: N = 5 * gh * gw
+#endif
 };
 int launch_edge_stats(const EdgeArgs& a, cudaStream_t st);
 int launch_edge_apply(const EdgeArgs& a, cudaStream_t st);

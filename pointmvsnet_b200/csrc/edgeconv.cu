@@ -398,8 +398,18 @@ static int launch_edge(const EdgeArgs& a, cudaStream_t st) {
 #undef PMVS_EDGE_CASE
   return check_launch(APPLY ? "edge_apply_kernel" : "edge_stats_kernel", st);
 }
+#if PMVS_EDGE_TILE
+#include "edge_tile.cuh"
+int launch_edge_stats(const EdgeArgs& a, cudaStream_t st) {
+  return a.cand ? launch_edge_tile<false>(a, st) : launch_edge<false>(a, st);
+}
+int launch_edge_apply(const EdgeArgs& a, cudaStream_t st) {
+  return a.cand ? launch_edge_tile<true>(a, st) : launch_edge<true>(a, st);
+}
+#else
 int launch_edge_stats(const EdgeArgs& a, cudaStream_t st) { return launch_edge<false>(a, st); }
 int launch_edge_apply(const EdgeArgs& a, cudaStream_t st) { return launch_edge<true>(a, st); }
+#endif
 
 // =======================================================================================
 // flow head: BN+ReLU of the 16-channel MLP output, Conv1d 16->1, softmax(-flow) over the 5

@@ -44,7 +44,11 @@ __constant__ signed char c_ring3[9][2] = {{0, 0}, {-1, 0}, {0, -1}, {0, 1}, {1, 
 
 template <int KS, int K, typename IdxT>
 __global__ void __launch_bounds__(KNN_TX* KNN_TY* KNN_TD)
-    knn3d_kernel(const float* __restrict__ xyz, IdxT* __restrict__ idx_out, int D, int H, int W, int dtiles) {
+    knn3d_kernel(const float* __restrict__ xyz, IdxT* __restrict__ idx_out, int D, int H, int W, int dtiles
+#if PMVS_EDGE_TILE
+                 , unsigned char* __restrict__ cand_out  // optional [clouds*D*H*W, K] candidate ids (K == 16)
+#endif
+    ) {
   constexpr int HK = KS / 2;
   constexpr int SX = KNN_TX + 2 * HK, SY = KNN_TY + 2 * HK, SZ = KNN_TD + 2 * HK;
   __shared__ float tile[3][SZ][SY][SX];
@@ -132,6 +136,21 @@ __global__ void __launch_bounds__(KNN_TX* KNN_TY* KNN_TD)
   for (int p = 0; p < K; p += VEC) {
     *reinterpret_cast<int4*>(dst + p) = *reinterpret_cast<const int4*>(&vals[p]);
   }
+#if PMVS_EDGE_TILE
+  if (K == 16 && cand_out != nullptr) {
+    // candidate id of every pick, 255 when the candidate lies outside the grid (its linear index is
+    // clamped / aliases another row, torch_utils.py:51-59, and must be taken from idx_out)
+    unsigned w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+      const int j = bi[p];
+      const int od = j / (KS * KS) - HK, oh = (j % (KS * KS)) / KS - HK, ow = j % KS - HK;
+      const bool in = z + od >= 0 && z + od < D && y + oh >= 0 && y + oh < H && x + ow >= 0 && x + ow < W;
+      w4[p >> 2] |= (in ? (unsigned)j : 255u) << (8 * (p & 3));
+    }
+    *reinterpret_cast<uint4*>(cand_out + ((long long)cloud * DHW + n) * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+  }
+#endif
 }
 
 template <int KS, int K>
@@ -141,10 +160,17 @@ static int launch_ks_k(const float* xyz, int64_t* idx64, int32_t* idx32, int clo
   dim3 block(KNN_TX, KNN_TY, KNN_TD);
   dim3 grid(cdiv(W, KNN_TX), cdiv(H, KNN_TY), clouds * dtiles);
   prof_begin("knn3d", st);
+#if PMVS_EDGE_TILE
+  if (idx32)
+    knn3d_kernel<KS, K, int32_t><<<grid, block, 0, st>>>(xyz, idx32, D, H, W, dtiles, nullptr);
+  else
+    knn3d_kernel<KS, K, int64_t><<<grid, block, 0, st>>>(xyz, idx64, D, H, W, dtiles, nullptr);
+#else
   if (idx32)
     knn3d_kernel<KS, K, int32_t><<<grid, block, 0, st>>>(xyz, idx32, D, H, W, dtiles);
   else
     knn3d_kernel<KS, K, int64_t><<<grid, block, 0, st>>>(xyz, idx64, D, H, W, dtiles);
+#endif
   return check_launch("knn3d_kernel", st);
 }
 
@@ -161,6 +187,22 @@ static int launch_ks(const float* xyz, int64_t* idx64, int32_t* idx32, int cloud
   set_error("knn3d: unsupported knn=%d (supported: 4, 8, 16, 20, 32)", knn);
   return PMVS_ERR_ARG;
 }
+
+#if PMVS_EDGE_TILE
+int launch_knn3d_cand(const float* xyz, int32_t* idx32, unsigned char* cand, int clouds, int D, int H, int W,
+                      cudaStream_t st) {
+  PMVS_REQUIRE(xyz && idx32 && cand, "knn3d_cand: NULL pointer");
+  PMVS_REQUIRE(clouds > 0 && D > 0 && H > 0 && W > 0, "knn3d: empty input");
+  PMVS_REQUIRE((long long)clouds * cdiv(D, KNN_TD) <= 65535, "knn3d: too many clouds");
+  PMVS_REQUIRE((long long)D * H * W < (1ll << 31), "knn3d: cloud too large for int32 indices");
+  const int dtiles = cdiv(D, KNN_TD);
+  dim3 block(KNN_TX, KNN_TY, KNN_TD);
+  dim3 grid(cdiv(W, KNN_TX), cdiv(H, KNN_TY), clouds * dtiles);
+  prof_begin("knn3d", st);
+  knn3d_kernel<5, 16, int32_t><<<grid, block, 0, st>>>(xyz, idx32, D, H, W, dtiles, cand);
+  return check_launch("knn3d_kernel", st);
+}
+#endif
 
 int launch_knn3d(const float* xyz, int64_t* idx64, int32_t* idx32, int clouds, int D, int H, int W, int ksize,
                  int knn, cudaStream_t st) {
