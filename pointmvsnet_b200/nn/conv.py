@@ -2,29 +2,35 @@
 (``conv.weight``, ``bn.*``) match the reference so its checkpoints load unchanged; inside
 PointFlow the arithmetic is done by the fused sm_100a kernels, this forward is the
 stock-library path for stand-alone use."""
-from torch import nn
 import torch.nn.functional as F
+from torch import nn
 
-from .init import init_uniform, init_bn
+from .init import init_bn, init_uniform
 
 
 class Conv1d(nn.Module):
-    def __init__(self, in_channels, out_channels, kernel_size, relu=True, bn=True, bn_momentum=0.1, **kwargs):
-        super(Conv1d, self).__init__()
-        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size, bias=(not bn), **kwargs)
-        self.bn = nn.BatchNorm1d(out_channels, momentum=bn_momentum) if bn else None
-        self.relu = relu
-        self.init_weights()
+    """1-D convolution, then (optionally) train-mode-aware BatchNorm1d and ReLU.
 
-    def forward(self, x):
-        x = self.conv(x)
-        if self.bn is not None:
-            x = self.bn(x)
-        if self.relu:
-            x = F.relu(x, inplace=True)
-        return x
+    With ``bn=True`` the convolution has no bias (the BN shift replaces it), as in the reference."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, relu=True, bn=True, bn_momentum=0.1, **kwargs):
+        super().__init__()
+        self.relu = bool(relu)
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size, bias=not bn, **kwargs)
+        init_uniform(self.conv)
+        self.bn = None
+        if bn:
+            self.bn = nn.BatchNorm1d(out_channels, momentum=bn_momentum)
+            init_bn(self.bn)
 
     def init_weights(self):
-        init_uniform(self.conv)
+        """Re-draw the parameters (Xavier-uniform weights, BN affine = (1, 0))."""
+        for module, init in ((self.conv, init_uniform), (self.bn, init_bn)):
+            if module is not None:
+                init(module)
+
+    def forward(self, x):
+        y = self.conv(x)
         if self.bn is not None:
-            init_bn(self.bn)
+            y = self.bn(y)
+        return F.relu(y) if self.relu else y

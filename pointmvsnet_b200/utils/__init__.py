@@ -1,0 +1,1 @@
+"""Mirrors of the reference utils the PointFlow path touches: feature fetcher, kNN, file formats."""
