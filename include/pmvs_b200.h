@@ -53,6 +53,22 @@ unsigned long long pmvs_launch_count(void);
 int pmvs_set_gemm_mode(int mode);
 int pmvs_get_gemm_mode(void);
 
+/* Implementation switches of the fused path (process-wide, like the GEMM mode; for A/B measurements
+ * and bisecting - every setting computes the same results):
+ *   PMVS_OPT_EDGE   EdgeConv statistics/apply: 0 = 16 L2 gathers per point (round-1 kernels),
+ *                   1 = TMA halo tile 8x4 pixels x 5 layers in shared memory, 2 = 16x4 tile
+ *   PMVS_OPT_KNN    0 = sorted insertion, 1 = batched sorting network + bitonic merge (k=5,knn=16)
+ *   PMVS_OPT_FETCH  0 = 4 taps per (hypothesis, view), 1 = hypotheses share the texel quad
+ *   PMVS_OPT_GEMM   0 = points-as-M, shared-memory operands, 1 = weights in TMEM / points as N
+ *   PMVS_OPT_DEBUG_IDX  1 = also materialise int32 neighbour indices in the workspace */
+#define PMVS_OPT_EDGE 1
+#define PMVS_OPT_KNN 2
+#define PMVS_OPT_FETCH 3
+#define PMVS_OPT_GEMM 4
+#define PMVS_OPT_DEBUG_IDX 5
+int pmvs_set_option(int key, int value);
+int pmvs_get_option(int key);
+
 /* Per-launch CUDA-event timing for bench.py's roofline: while enabled every kernel launch of
  * this library is bracketed by two events on its stream (do not enable during graph capture).
  * pmvs_profile_collect synchronises, writes '\n'-separated kernel names and durations (ms)
@@ -197,9 +213,12 @@ int pmvs_pyramid_to_channels_last(const float* nchw, float* nhwc, int BV, int C,
 
 /* Debug/inspection view of the workspace after pmvs_point_flow_iter (used by the parity
  * tests to compare every stage with the oracle).  Returns byte offsets into workspace:
- * off[0]=feature [S,B,N,136], off[1]=xyz [S,B,3,N], off[2]=idx32 [S,B,N,16],
- * off[3]=edge cat [S,B,N,224], off[4]=mlp h2 [S,B,N,16]; S = ratio^2, N = 5*h'*w'. */
-int pmvs_point_flow_debug_offsets(const pmvs_flow_shape* shape, size_t off[8]);
+ * off[0]=feature [S,B,N,136], off[1]=xyz [S,B,3,N], off[2]=idx32 [S,B,N,16] (valid if off[9]),
+ * off[3]=edge cat [S,B,N,224], off[4]=mlp h2 [S,B,N,16], off[5]=LE scratch, off[6]=BN sums,
+ * off[7]=total bytes, off[8]=kNN candidate ids [S,B,N,16] uint8 (id = d*25+h*5+w of the 5x5x5
+ * window, bit 7 = candidate outside the grid), off[9]=1 if idx32 was materialised;
+ * S = ratio^2, N = 5*h'*w'. */
+int pmvs_point_flow_debug_offsets(const pmvs_flow_shape* shape, size_t off[10]);
 
 #ifdef __cplusplus
 }

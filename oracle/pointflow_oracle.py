@@ -272,11 +272,16 @@ def cal_sub_flow(xyz, feature, interval, params, knn=16, return_stages=False, kn
 # a2-a9: hypothesis points, multi-view fetch, variance  (model.py:150-204)
 # --------------------------------------------------------------------------- #
 def build_point_features(depth, interval, image_scale, pyramids, cam_params, mean, std,
-                         img_hw, is_test=True):
+                         img_hw, is_test=True, sub=None):
     """depth [B,1,hp,wp] (previous estimate), interval [B], pyramids = list of
     [B,V,C,hl,wl] (conv1, conv2, conv3), cam_params [B,V,2,4,4], mean/std [B,3],
     img_hw = (H, W) of the input images.
-    Returns feature [B,136,5,h,w], xyz [B,3,5,h,w], depth_up [B,1,h,w]."""
+    Returns feature [B,136,5,h,w], xyz [B,3,5,h,w], depth_up [B,1,h,w].
+
+    ``sub=(i, j, ratio)`` evaluates only the pixels (y*ratio+i, x*ratio+j) of ONE strided
+    sub-cloud (model.py:236-255) -- same operations on a subset of the (independent) points, so
+    that one sub-cloud of a large configuration can be checked without the full-size tensors;
+    the returned tensors then have the sub-grid size (h/ratio, w/ratio)."""
     B, V = cam_params.shape[:2]
     H, W = img_hw
     ext = cam_params[:, :, 0, :3, :4]  # model.py:54
@@ -291,16 +296,27 @@ def build_point_features(depth, interval, image_scale, pyramids, cam_params, mea
     K[:, :, :2, :3] *= image_scale if is_test else 4 * image_scale
     grid = get_pixel_grids(h, w).view(1, 1, 3, -1).expand(B, 1, 3, -1)
     uv = torch.matmul(torch.inverse(K[:, 0]).unsqueeze(1), grid)  # model.py:169-170
+    oh, ow = h, w
+    if sub is not None:
+        si, sj, sr = sub
+        sel = (torch.arange(si, h, sr).view(-1, 1) * w + torch.arange(sj, w, sr).view(1, -1)).reshape(-1)
+        uv = uv[..., sel]
+        depth = depth.reshape(B, 1, -1)[..., sel].view(B, 1, h // sr, w // sr)
+        oh, ow = h // sr, w // sr
     feats, xyzs = [], []
+    # model.py:180-185 resizes every level inside the hypothesis loop; the result does not depend
+    # on the hypothesis, so it is computed once here (identical values)
+    resized = []
+    for level in pyramids:
+        c, hl, wl = level.shape[2:]
+        resized.append(F.interpolate(level.reshape(-1, c, hl, wl), (h, w), mode="bilinear",
+                                     align_corners=False).view(B, V, c, h, w))
     for m in HYPOTHESES:  # model.py:173
         dm = depth + interval.view(-1, 1, 1, 1) * m
         cam_pts = uv * dm.view(B, 1, 1, -1)
         world = torch.matmul(R_inv[:, 0:1], cam_pts - t[:, 0:1]).transpose(1, 2).reshape(B, 3, -1)
         per_level = []
-        for level in pyramids:  # model.py:180-190
-            c, hl, wl = level.shape[2:]
-            lv = F.interpolate(level.reshape(-1, c, hl, wl), (h, w), mode="bilinear",
-                               align_corners=False).view(B, V, c, h, w)
+        for lv in resized:  # model.py:180-190
             pf = feature_fetch(lv, world, K, ext)
             avg = pf.mean(dim=1)
             avg2 = (pf ** 2).mean(dim=1)
@@ -309,8 +325,8 @@ def build_point_features(depth, interval, image_scale, pyramids, cam_params, mea
         per_level.append(xyz.repeat(1, 8, 1))  # model.py:194
         feats.append(torch.cat(per_level, dim=1))
         xyzs.append(xyz)
-    feature = torch.stack(feats, dim=2).view(B, -1, len(HYPOTHESES), h, w)  # model.py:202
-    xyz = torch.stack(xyzs, dim=2).view(B, 3, len(HYPOTHESES), h, w)  # model.py:203-204
+    feature = torch.stack(feats, dim=2).view(B, -1, len(HYPOTHESES), oh, ow)  # model.py:202
+    xyz = torch.stack(xyzs, dim=2).view(B, 3, len(HYPOTHESES), oh, ow)  # model.py:203-204
     return feature, xyz, depth
 
 
@@ -352,13 +368,18 @@ def coarse_cost_volume(feature_list, cam_params, is_test=True):
 # a1: one PointFlow iteration  (model.py:150-295)
 # --------------------------------------------------------------------------- #
 def point_flow(depth, interval, image_scale, pyramids, cam_params, mean, std, img_hw,
-               params, is_test=True, knn=16, return_stages=False, knn_fn=None):
-    """Returns (flow_result [B,1,h,w], flow_prob [B,5,h,w]) for one iteration."""
-    feature, xyz, depth_up = build_point_features(depth, interval, image_scale, pyramids,
-                                                  cam_params, mean, std, img_hw, is_test)
-    B, _, M, h, w = xyz.shape
+               params, is_test=True, knn=16, return_stages=False, knn_fn=None, sub=None):
+    """Returns (flow_result [B,1,h,w], flow_prob [B,5,h,w]) for one iteration.
+    ``sub=(i, j)`` (test mode, ratio > 1): only that strided sub-cloud is evaluated and the
+    results have the sub-grid size -- one of the ratio^2 independent calls of model.py:236-267."""
     ratio = int(image_scale * 8) if is_test else 1
-    if ratio <= 1:  # model.py:231-234 (test, scale 0.125) / :271-293 (train)
+    if sub is not None:
+        assert ratio > 1
+        sub = (sub[0], sub[1], ratio)
+    feature, xyz, depth_up = build_point_features(depth, interval, image_scale, pyramids,
+                                                  cam_params, mean, std, img_hw, is_test, sub=sub)
+    B, _, M, h, w = xyz.shape
+    if ratio <= 1 or sub is not None:  # model.py:231-234 (test, scale 0.125) / :271-293 (train)
         flow, prob = cal_sub_flow(xyz, feature, interval, params, knn, knn_fn=knn_fn)
     else:  # model.py:236-267
         sh, sw = h // ratio, w // ratio

@@ -55,6 +55,8 @@ _sig("pmvs_last_error", C.c_char_p, [])
 _sig("pmvs_launch_count", C.c_ulonglong, [])
 _sig("pmvs_set_gemm_mode", I, [I])
 _sig("pmvs_get_gemm_mode", I, [])
+_sig("pmvs_set_option", I, [I, I])
+_sig("pmvs_get_option", I, [I])
 _sig("pmvs_profile_enable", I, [I])
 _sig("pmvs_profile_collect", I, [C.c_char_p, C.c_size_t, P, I])
 _sig("pmvs_gather_knn_forward", I, [P, P, P, I, I, I, I, P])
@@ -71,10 +73,10 @@ _sig("pmvs_point_flow_workspace_bytes", C.c_size_t, [C.POINTER(FlowShape)])
 _sig("pmvs_point_flow_iter", I, [C.POINTER(FlowShape), C.POINTER(FlowWeights), C.POINTER(C.c_void_p * 3),
                                  P, P, P, P, P, P, P, P, C.c_size_t, P])
 _sig("pmvs_pyramid_to_channels_last", I, [P, P, I, I, I, I, P])
-_sig("pmvs_point_flow_debug_offsets", I, [C.POINTER(FlowShape), C.POINTER(C.c_size_t * 8)])
+_sig("pmvs_point_flow_debug_offsets", I, [C.POINTER(FlowShape), C.POINTER(C.c_size_t * 10)])
 
 EXPORTED = [
-    "pmvs_version", "pmvs_last_error", "pmvs_launch_count", "pmvs_profile_enable", "pmvs_profile_collect", "pmvs_set_gemm_mode", "pmvs_get_gemm_mode", "pmvs_gather_knn_forward",
+    "pmvs_version", "pmvs_last_error", "pmvs_launch_count", "pmvs_set_option", "pmvs_get_option", "pmvs_profile_enable", "pmvs_profile_collect", "pmvs_set_gemm_mode", "pmvs_get_gemm_mode", "pmvs_gather_knn_forward",
     "pmvs_gather_knn_backward", "pmvs_knn3d", "pmvs_feature_fetch", "pmvs_feature_fetch_backward",
     "pmvs_cost_volume", "pmvs_transpose", "pmvs_idx64_to_idx32", "pmvs_edgeconv_pm", "pmvs_linear_pm", "pmvs_point_flow_workspace_bytes",
     "pmvs_point_flow_iter", "pmvs_pyramid_to_channels_last", "pmvs_point_flow_debug_offsets",
@@ -129,3 +131,27 @@ def profile_collect(max_records=65536):
 def set_gemm_mode(mode):
     """0: fp32 SIMT, 1: TF32 tensor cores, 3: 3xTF32 tensor cores (default)"""
     check(lib.pmvs_set_gemm_mode(int(mode)))
+
+
+# implementation switches (include/pmvs_b200.h PMVS_OPT_*): which kernel family serves a stage of the fused path
+OPTIONS = {"edge": 1, "knn": 2, "fetch": 3, "gemm": 4, "debug_idx": 5}
+
+
+def set_option(name, value):
+    check(lib.pmvs_set_option(OPTIONS[name], int(value)))
+
+
+def get_option(name):
+    return int(lib.pmvs_get_option(OPTIONS[name]))
+
+
+def _options_from_env():
+    """PMVS_OPTIONS="edge=0,knn=0" selects the older kernel families (A/B measurements, bisecting)."""
+    spec = os.environ.get("PMVS_OPTIONS", "")
+    for item in spec.split(","):
+        if "=" in item:
+            k, v = item.split("=", 1)
+            set_option(k.strip(), int(v))
+
+
+_options_from_env()

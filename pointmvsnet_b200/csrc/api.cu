@@ -22,6 +22,10 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
+// run-time implementation switches (common.cuh OPT_*); process-wide like the GEMM mode
+static std::atomic<int> g_opt[OPT_COUNT];
+int opt(int key) { return (key >= 0 && key < OPT_COUNT) ? g_opt[key].load(std::memory_order_relaxed) : 0; }
+
 // ---- optional per-launch event timing ------------------------------------------------------
 struct ProfRec {
   const char* name;
@@ -127,11 +131,14 @@ struct FlowPlan {
   size_t R;  // rows = S * B * N
   size_t cam, feature, xyz, idx, le, ecat, h0, h1, h2, stats, total;
   size_t warp_src;     // the pyramid levels resized to the flow grid, [B,V,h,w,112]
-#if PMVS_EDGE_TILE
   size_t cand;         // [R, 16] bytes: kNN candidate ids for the tile EdgeConv kernels
-#endif
-  size_t st_ec[3], st_mlp[3];  // offsets (in doubles) inside the stats region
+  // offsets (in doubles) inside the stats region.  Per EdgeConv layer and group 6*cout doubles: st_ec = 4*cout
+  // (gather path: [sum_c | sumsq_c | sum_n | sumsq_n]; tile path: column sums / sums of squares of the
+  // 2*cout GEMM outputs), st_ecn = 2*cout ([sum_n | sumsq_n] of the tile path)
+  size_t st_ec[3], st_ecn[3], st_mlp[3];
+  size_t st_ticket;    // 3*S unsigned arrival counters of the tile statistics kernels (inside the zeroed region)
   size_t stats_doubles;
+  size_t coef;         // [3][S][6*64] floats: per (layer, group) BatchNorm coefficients of the tile apply kernels
 };
 
 static int make_plan(const pmvs_flow_shape* s, FlowPlan& p) {
@@ -161,16 +168,19 @@ static int make_plan(const pmvs_flow_shape* s, FlowPlan& p) {
   p.h1 = o; o += align_up(p.R * 64 * 4);
   p.h2 = o; o += align_up(p.R * 16 * 4);
   p.warp_src = o; o += align_up(warp_source_bytes(s->B, s->V, s->flow_h, s->flow_w));
-#if PMVS_EDGE_TILE
   p.cand = o; o += align_up(p.R * PMVS_KNN);
-#endif
   size_t d = 0;
   const int ec_cout[3] = {32, 32, 64};
   const int mlp_cout[3] = {64, 64, 16};
-  for (int l = 0; l < 3; ++l) { p.st_ec[l] = d; d += (size_t)p.S * 4 * ec_cout[l]; }
+  for (int l = 0; l < 3; ++l) {
+    p.st_ec[l] = d; d += (size_t)p.S * 4 * ec_cout[l];
+    p.st_ecn[l] = d; d += (size_t)p.S * 2 * ec_cout[l];
+  }
   for (int l = 0; l < 3; ++l) { p.st_mlp[l] = d; d += (size_t)p.S * 2 * mlp_cout[l]; }
+  p.st_ticket = d; d += (3 * (size_t)p.S + 1) / 2 + 1;
   p.stats_doubles = d;
   p.stats = o; o += align_up(d * 8);
+  p.coef = o; o += align_up(3 * (size_t)p.S * 6 * 64 * sizeof(float));
   p.total = o;
   return PMVS_OK;
 }
@@ -182,6 +192,13 @@ using namespace pmvs;
 extern "C" int pmvs_version(void) { return 100; }
 extern "C" const char* pmvs_last_error(void) { return g_err; }
 extern "C" unsigned long long pmvs_launch_count(void) { return g_launches.load(); }
+
+extern "C" int pmvs_set_option(int key, int value) {
+  PMVS_REQUIRE(key > 0 && key < OPT_COUNT, "set_option: unknown key %d", key);
+  g_opt[key].store(value);
+  return PMVS_OK;
+}
+extern "C" int pmvs_get_option(int key) { return opt(key); }
 
 extern "C" int pmvs_profile_enable(int on) {
   g_prof_on.store(on ? 1 : 0);
@@ -304,11 +321,13 @@ extern "C" size_t pmvs_point_flow_workspace_bytes(const pmvs_flow_shape* shape) 
   return p.total;
 }
 
-extern "C" int pmvs_point_flow_debug_offsets(const pmvs_flow_shape* shape, size_t off[8]) {
+extern "C" int pmvs_point_flow_debug_offsets(const pmvs_flow_shape* shape, size_t off[10]) {
   FlowPlan p;
   PMVS_TRY(make_plan(shape, p));
   off[0] = p.feature; off[1] = p.xyz; off[2] = p.idx; off[3] = p.ecat; off[4] = p.h2;
   off[5] = p.le; off[6] = p.stats; off[7] = p.total;
+  off[8] = p.cand;
+  off[9] = (opt(OPT_EDGE) == 0 || opt(OPT_DEBUG_IDX) != 0) ? 1 : 0;  // 1: idx32 is materialised, 0: only cand
   return PMVS_OK;
 }
 
@@ -351,7 +370,7 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
 
   // model.py:184: every level of every view resized to the flow grid, once per iteration
   float* warp_src = (float*)(ws + p.warp_src);
-  PMVS_TRY(launch_warp_source(pyramids_cl, shape->pyr_h, shape->pyr_w, warp_src, B * shape->V, shape->flow_h,
+  PMVS_TRY(launch_warp_source(pyramids_cl, shape->pyr_h, shape->pyr_w, warp_src, B, shape->V, shape->flow_h,
                               shape->flow_w, st));
   FusedFetchParams f{};
   f.src = warp_src;
@@ -360,12 +379,14 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
   f.ratio = shape->ratio;
   PMVS_TRY(launch_fused_fetch(f, st));
 
-#if PMVS_EDGE_TILE
+  // a10: neighbour lists.  The tile EdgeConv path consumes 1-byte candidate ids; the int32 row indices are only
+  // materialised for the gather path (or on request, for the tests)
+  const int edge_impl = opt(OPT_EDGE);
   unsigned char* cand = (unsigned char*)(ws + p.cand);
-  PMVS_TRY(launch_knn3d_cand(xyz, idx, cand, S * B, PMVS_NUM_HYP, p.hs, p.ws, st));
-#else
-  PMVS_TRY(launch_knn3d(xyz, nullptr, idx, S * B, PMVS_NUM_HYP, p.hs, p.ws, PMVS_NUM_HYP, PMVS_KNN, st));
-#endif
+  if (edge_impl != 0)
+    PMVS_TRY(launch_knn3d_cand(xyz, opt(OPT_DEBUG_IDX) ? idx : nullptr, cand, S * B, PMVS_NUM_HYP, p.hs, p.ws, st));
+  else
+    PMVS_TRY(launch_knn3d(xyz, nullptr, idx, S * B, PMVS_NUM_HYP, p.hs, p.ws, PMVS_NUM_HYP, PMVS_KNN, st));
 
   // flow_edge_conv (model.py:213-216): EdgeConvNoC(136,32), EdgeConv(32,32), EdgeConv(64,64)
   const int cin[3] = {136, 32, 64}, cout[3] = {32, 32, 64}, in_off[3] = {0, 0, 32}, out_off[3] = {0, 32, 96};
@@ -375,16 +396,27 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
     g.ldx = l == 0 ? PMVS_FEAT_CH : 224;
     g.w = wts->ec_w12[l]; g.y = le; g.ldy = 2 * cout[l];
     g.groups = S; g.rows_per_group = rows_per_group; g.cin = cin[l]; g.cout = 2 * cout[l]; g.eps = wts->eps;
+    if (edge_impl != 0) g.out_stats = stats + p.st_ec[l];  // column sums of LE: the central half's BN statistics
     PMVS_TRY(launch_gemm(g, st));
-    EdgeArgs e{};
-    e.le = le; e.idx = idx; e.stats = stats + p.st_ec[l]; e.gamma = wts->ec_gamma[l]; e.beta = wts->ec_beta[l];
-    e.eps = wts->eps; e.concat_central = l > 0; e.out = ecat + out_off[l]; e.ldo = 224; e.groups = S;
-    e.rows_per_group = rows_per_group; e.N = p.N; e.K = PMVS_KNN; e.cout = cout[l];
-#if PMVS_EDGE_TILE
-    e.cand = cand; e.gh = p.hs; e.gw = p.ws;
-#endif
-    PMVS_TRY(launch_edge_stats(e, st));
-    PMVS_TRY(launch_edge_apply(e, st));
+    if (edge_impl != 0) {
+      EdgeTileArgs e{};
+      e.le = le; e.cand = cand; e.cstats = stats + p.st_ec[l]; e.nstats = stats + p.st_ecn[l];
+      e.coef = (float*)(ws + p.coef) + (size_t)l * S * 6 * 64;
+      e.ticket = (unsigned*)(stats + p.st_ticket) + (size_t)l * S;
+      e.gamma = wts->ec_gamma[l]; e.beta = wts->ec_beta[l]; e.eps = wts->eps; e.concat_central = l > 0;
+      e.out = ecat + out_off[l]; e.ldo = 224; e.groups = S; e.clouds_per_group = B; e.gh = p.hs; e.gw = p.ws;
+      e.cout = cout[l];
+      const int tile_w = edge_impl == 2 ? 16 : 8;
+      PMVS_TRY(launch_edge_tile_stats(e, tile_w, st));
+      PMVS_TRY(launch_edge_tile_apply(e, tile_w, st));
+    } else {
+      EdgeArgs e{};
+      e.le = le; e.idx = idx; e.stats = stats + p.st_ec[l]; e.gamma = wts->ec_gamma[l]; e.beta = wts->ec_beta[l];
+      e.eps = wts->eps; e.concat_central = l > 0; e.out = ecat + out_off[l]; e.ldo = 224; e.groups = S;
+      e.rows_per_group = rows_per_group; e.N = p.N; e.K = PMVS_KNN; e.cout = cout[l];
+      PMVS_TRY(launch_edge_stats(e, st));
+      PMVS_TRY(launch_edge_apply(e, st));
+    }
   }
 
   // flow_mlp (model.py:40-43,220): 224 -> 64 -> 64 -> 16 -> 1, BN batch statistics per sub-cloud
@@ -418,17 +450,24 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
     if (wts->ec_run_mean[l] && wts->ec_run_var[l]) {
       const int c = cout[l];
       const double* sl = stats + p.st_ec[l];
+      const bool tile = edge_impl != 0;
       if (l > 0) {  // central half: channels [0, c)
         RunUpdate& u = rb.u[rb.n++];
         u.stats = sl; u.run_mean = wts->ec_run_mean[l]; u.run_var = wts->ec_run_var[l]; u.C = c;
         // statistics of a value repeated K times equal the per-point statistics; only the
         // unbiased correction sees the count, which is N*K as in the reference's BN input
-        u.off_sum = 0; u.off_sq = c; u.gstride = 4 * c; u.count = (double)rows_per_group;
+        u.off_sum = 0; u.off_sq = tile ? 2 * c : c; u.gstride = 4 * c; u.count = (double)rows_per_group;
         u.ncorr = (double)rows_per_group * PMVS_KNN;
       }
       RunUpdate& u = rb.u[rb.n++];
-      u.stats = sl; u.run_mean = wts->ec_run_mean[l] + (l > 0 ? c : 0); u.run_var = wts->ec_run_var[l] + (l > 0 ? c : 0);
-      u.C = c; u.off_sum = 2 * c; u.off_sq = 3 * c; u.gstride = 4 * c; u.count = (double)rows_per_group * PMVS_KNN;
+      u.run_mean = wts->ec_run_mean[l] + (l > 0 ? c : 0); u.run_var = wts->ec_run_var[l] + (l > 0 ? c : 0);
+      u.C = c;
+      if (tile) {
+        u.stats = stats + p.st_ecn[l]; u.off_sum = 0; u.off_sq = c; u.gstride = 2 * c;
+      } else {
+        u.stats = sl; u.off_sum = 2 * c; u.off_sq = 3 * c; u.gstride = 4 * c;
+      }
+      u.count = (double)rows_per_group * PMVS_KNN;
       u.ncorr = u.count; u.nbt = wts->ec_nbt[l];
     }
   }

@@ -49,17 +49,8 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-// Packed fp32 pairs (sm_100a FFMA2 / FADD2 / FMUL2; IEEE rn per lane, i.e. bit-identical to the scalar
-// ops).  EXPERIMENTAL: compiled in only with -DPMVS_F32X2=1 (bash build.sh -DPMVS_F32X2=1); the default
-// build does not contain them until they have been measured on a B200.
-#ifndef PMVS_F32X2
-#define PMVS_F32X2 0
-#endif
-// EXPERIMENTAL shared-memory-tile EdgeConv kernels (csrc/edge_tile.cuh), same rule: -DPMVS_EDGE_TILE=1 only
-#ifndef PMVS_EDGE_TILE
-#define PMVS_EDGE_TILE 0
-#endif
-#if PMVS_F32X2
+// Packed fp32 pairs (sm_100a FFMA2 / FADD2 / FMUL2: IEEE rn per lane, i.e. bit-identical to the scalar
+// operations, two lanes per issue slot).
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float a, float b) {
   f32x2 r;
@@ -87,7 +78,33 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-#endif
+
+// ---- run-time implementation switches (pmvs_set_option; api.cu) -------------------------------
+enum {
+  OPT_EDGE = 1,   // EdgeConv statistics/apply of the fused path: 0 = L2 gathers (edge_kernel), 1 = TMA halo tile 8x4x5,
+                  // 2 = TMA halo tile 16x4x5
+  OPT_KNN = 2,    // 0 = sorted insertion (round 1), 1 = batched sort + bitonic merge
+  OPT_FETCH = 3,  // 0 = 4 taps per (hypothesis, view), 1 = hypotheses of a pixel share the texel quad when they can
+  OPT_GEMM = 4,   // 0 = points-as-M shared-memory operands (round 1), 1 = weights in TMEM, points as N, persistent
+  OPT_DEBUG_IDX = 5,  // 1 = the fused path also materialises the int32 neighbour indices (tests)
+  OPT_COUNT = 16
+};
+int opt(int key);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device)
+template <typename K>
+inline int ensure_dyn_smem(K kernel, int bytes, unsigned long long& done_mask, const char* what) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) dev = 0;
+  if (done_mask & (1ull << dev)) return PMVS_OK;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: cannot reserve %d bytes of shared memory", what, bytes);
+    return PMVS_ERR_CUDA;
+  }
+  done_mask |= 1ull << dev;
+  return PMVS_OK;
+}
 
 // BatchNorm (train mode) per-channel parameters derived from fp64 sums.
 struct BnCoef {
@@ -108,11 +125,10 @@ __device__ __forceinline__ float bn_apply(float x, float mean, float invstd, flo
 }
 
 // ---- internal launchers shared between translation units ---------------------------
-#if PMVS_EDGE_TILE
-// knn3d with the additional 1-byte candidate-id output the tile kernels consume (ksize 5, knn 16, int32)
+// knn3d of the fused path (ksize 5, knn 16): 1-byte candidate ids [clouds*D*H*W, 16] (bit 7 set = the candidate lies
+// outside the grid, torch_utils.py:44,51-59) and, optionally (idx32 != NULL), the int32 linear indices
 int launch_knn3d_cand(const float* xyz, int32_t* idx32, unsigned char* cand, int clouds, int D, int H, int W,
                       cudaStream_t st);
-#endif
 int launch_knn3d(const float* xyz, int64_t* idx64, int32_t* idx32, int clouds, int D, int H, int W,
                  int ksize, int knn, cudaStream_t st);
 int launch_transpose(const float* in, float* out, int batch, int R, int C, cudaStream_t st);
@@ -136,6 +152,8 @@ struct GemmArgs {
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
 // tcgen05 path; returns -1 when it does not apply (shape / alignment / mode) so the caller falls back
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t st, const char* name);
+// second-generation tcgen05 path (gemm_ws.cu: weights in tensor memory, persistent, warp-specialised); 3xTF32 only
+int launch_gemm_ws(const GemmArgs& a, cudaStream_t st, const char* name);
 
 struct EdgeArgs {
   const float* le;  // [R, 2*cout]  (local | edge)
@@ -148,16 +166,32 @@ struct EdgeArgs {
   float* out;
   int ldo;
   int groups, rows_per_group, N, K, cout;
-#if PMVS_EDGE_TILE
-  const unsigned char* cand;  // [R, 16] kNN candidate ids (255 = out-of-grid pick, use idx); NULL = gather path
-  int gh, gw;                 // sub-grid size: N = 5 * gh * gw
-#endif
 };
 int launch_edge_stats(const EdgeArgs& a, cudaStream_t st);
 int launch_edge_apply(const EdgeArgs& a, cudaStream_t st);
 
+// EdgeConv statistics / apply on a structured cloud, neighbour rows gathered from a TMA-loaded
+// shared-memory halo tile (edge_tile.cu)
+struct EdgeTileArgs {
+  const float* le;            // [R, 2*cout]  (local | edge), R = groups * clouds_per_group * 5 * gh * gw
+  const unsigned char* cand;  // [R, 16] candidate ids from launch_knn3d_cand
+  const double* cstats;       // per group [sum(2*cout) | sumsq(2*cout)] of the LE columns (GEMM epilogue)
+  double* nstats;             // per group [sum_n(cout) | sumsq_n(cout)] of edge[idx] - local over (rows, K)
+  float* coef;                // per group 6*cout floats: BatchNorm coefficients, written by the last statistics CTA
+  unsigned* ticket;           // per group arrival counter of the statistics CTAs (zeroed by the caller)
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int concat_central;
+  float* out;
+  int ldo;
+  int groups, clouds_per_group, gh, gw, cout;
+};
+int launch_edge_tile_stats(const EdgeTileArgs& a, int tile_w, cudaStream_t st);
+int launch_edge_tile_apply(const EdgeTileArgs& a, int tile_w, cudaStream_t st);
+
 struct FusedFetchParams {
-  const float* src;         // warp source map [B,V,h,w,112]: the pyramid levels resized to the flow grid
+  const float* src;         // warp source map [B][V*h*w + 1][112]: pyramid levels resized to the flow grid + a zero texel
   const float* depth_prev;  // [B,1,hp,wp]
   const float* cam_blocks;  // [B, cam_block_floats(V)]
   float* feature;           // [S,B,N,136]
@@ -166,8 +200,8 @@ struct FusedFetchParams {
   int ppw, hs, ws, rlog2;   // set by the launcher: pixels per warp, sub-grid size, log2(ratio) or -1
 };
 // model.py:184 for the three levels at once: channels-last pyramids [B*V,hl,wl,16<<l] -> [B*V,h,w,112]
-int launch_warp_source(const float* const pyr[3], const int hl[3], const int wl[3], float* out, int BV, int h, int w,
-                       cudaStream_t st);
+int launch_warp_source(const float* const pyr[3], const int hl[3], const int wl[3], float* out, int B, int V, int h,
+                       int w, cudaStream_t st);
 size_t warp_source_bytes(int B, int V, int h, int w);
 int launch_cam_setup(const float* cam_params, const float* interval, const float* mean, const float* stdv,
                      float* blocks, int B, int V, float kscale, float iscale, cudaStream_t st);

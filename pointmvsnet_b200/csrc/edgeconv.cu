@@ -190,6 +190,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   else if (a.cin == 224 && a.cout == 64) ni = 3;
   else if (a.cin == 64 && a.cout == 64) ni = 4;
   else if (a.cin == 64 && a.cout == 16) ni = 5;
+  if (opt(OPT_GEMM) != 0 && pmvs_get_gemm_mode() == 3) {
+    const int rc = launch_gemm_ws(a, st, names[ni]);
+    if (rc >= 0) return rc;
+  }
   {
     const int rc = launch_gemm_tc(a, st, names[ni]);
     if (rc >= 0) return rc;
@@ -267,30 +271,6 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
       c0 = make_float4(fmaf(-(m.x + loc.x), A4.x, bt.x), fmaf(-(m.y + loc.y), A4.y, bt.y),
                        fmaf(-(m.z + loc.z), A4.z, bt.z), fmaf(-(m.w + loc.w), A4.w, bt.w));
     }
-#if PMVS_F32X2
-    // same arithmetic on fp32 pairs: apply 2 FFMA2 + 4 FMNMX + 2 FADD2, stats 6 packed ops per float4
-    const f32x2 A_lo = APPLY ? pack2(A4.x, A4.y) : 0ull, A_hi = APPLY ? pack2(A4.z, A4.w) : 0ull;
-    const f32x2 c_lo = APPLY ? pack2(c0.x, c0.y) : 0ull, c_hi = APPLY ? pack2(c0.z, c0.w) : 0ull;
-    const f32x2 l_lo = pack2(loc.x, loc.y), l_hi = pack2(loc.z, loc.w);
-    f32x2 o_lo = pack2(0.f, 0.f), o_hi = o_lo;
-    f32x2 n1_lo = pack2(sn1.x, sn1.y), n1_hi = pack2(sn1.z, sn1.w);
-    f32x2 n2_lo = pack2(sn2.x, sn2.y), n2_hi = pack2(sn2.z, sn2.w);
-    auto body = [&](int nb) {
-      const float4 e = ldg4(a.le + (cloud_base + nb) * LD + COUT + cl);
-      const f32x2 e_lo = pack2(e.x, e.y), e_hi = pack2(e.z, e.w);
-      if (APPLY) {
-        float t0, t1, t2, t3;
-        unpack2(fma2(e_lo, A_lo, c_lo), t0, t1);
-        unpack2(fma2(e_hi, A_hi, c_hi), t2, t3);
-        o_lo = add2(o_lo, pack2(fmaxf(t0, 0.f), fmaxf(t1, 0.f)));
-        o_hi = add2(o_hi, pack2(fmaxf(t2, 0.f), fmaxf(t3, 0.f)));
-      } else {
-        const f32x2 d_lo = sub2(e_lo, l_lo), d_hi = sub2(e_hi, l_hi);
-        n1_lo = add2(n1_lo, d_lo); n1_hi = add2(n1_hi, d_hi);
-        n2_lo = fma2(d_lo, d_lo, n2_lo); n2_hi = fma2(d_hi, d_hi, n2_hi);
-      }
-    };
-#else
     auto body = [&](int nb) {
       const float4 e = ldg4(a.le + (cloud_base + nb) * LD + COUT + cl);
       if (APPLY) {
@@ -306,7 +286,6 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
         sn2.z = fmaf(dz, dz, sn2.z); sn2.w = fmaf(dw, dw, sn2.w);
       }
     };
-#endif
     if constexpr (KT > 0) {
       static_assert(KT % 4 == 0, "KT");
       int nbs[KT];
@@ -320,14 +299,6 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
     } else {
       for (int k = 0; k < K; ++k) body(__ldg(ip + k));
     }
-#if PMVS_F32X2
-    if (APPLY) {
-      unpack2(o_lo, o.x, o.y); unpack2(o_hi, o.z, o.w);
-    } else {
-      unpack2(n1_lo, sn1.x, sn1.y); unpack2(n1_hi, sn1.z, sn1.w);
-      unpack2(n2_lo, sn2.x, sn2.y); unpack2(n2_hi, sn2.z, sn2.w);
-    }
-#endif
     if (APPLY) {
       const float kf = (float)K;
       float* orow = a.out + row * a.ldo;
@@ -340,7 +311,12 @@ __global__ void __launch_bounds__(E_THREADS) edge_kernel(const EdgeArgs a) {
         st4(orow + cl, c);
         orow += COUT;
       }
-      st4(orow + cl, make_float4(__fdiv_rn(o.x, kf), __fdiv_rn(o.y, kf), __fdiv_rn(o.z, kf), __fdiv_rn(o.w, kf)));
+      if ((K & (K - 1)) == 0) {  // power of two: x / K == x * (1 / K) exactly, without the division's slow path for 0
+        const float rk = 1.f / kf;
+        st4(orow + cl, make_float4(__fmul_rn(o.x, rk), __fmul_rn(o.y, rk), __fmul_rn(o.z, rk), __fmul_rn(o.w, rk)));
+      } else {
+        st4(orow + cl, make_float4(__fdiv_rn(o.x, kf), __fdiv_rn(o.y, kf), __fdiv_rn(o.z, kf), __fdiv_rn(o.w, kf)));
+      }
     } else {
       sc1.x += loc.x; sc1.y += loc.y; sc1.z += loc.z; sc1.w += loc.w;
       sc2.x = fmaf(loc.x, loc.x, sc2.x); sc2.y = fmaf(loc.y, loc.y, sc2.y);
@@ -398,18 +374,8 @@ static int launch_edge(const EdgeArgs& a, cudaStream_t st) {
 #undef PMVS_EDGE_CASE
   return check_launch(APPLY ? "edge_apply_kernel" : "edge_stats_kernel", st);
 }
-#if PMVS_EDGE_TILE
-#include "edge_tile.cuh"
-int launch_edge_stats(const EdgeArgs& a, cudaStream_t st) {
-  return a.cand ? launch_edge_tile<false>(a, st) : launch_edge<false>(a, st);
-}
-int launch_edge_apply(const EdgeArgs& a, cudaStream_t st) {
-  return a.cand ? launch_edge_tile<true>(a, st) : launch_edge<true>(a, st);
-}
-#else
 int launch_edge_stats(const EdgeArgs& a, cudaStream_t st) { return launch_edge<false>(a, st); }
 int launch_edge_apply(const EdgeArgs& a, cudaStream_t st) { return launch_edge<true>(a, st); }
-#endif
 
 // =======================================================================================
 // flow head: BN+ReLU of the 16-channel MLP output, Conv1d 16->1, softmax(-flow) over the 5
@@ -500,14 +466,28 @@ __global__ void bn_running_update_kernel(const RunUpdateBatch rb) {
   if (threadIdx.x == 0 && u.nbt != nullptr) *u.nbt += rb.groups;
   for (int c = threadIdx.x; c < u.C; c += blockDim.x) {
     float rm = u.run_mean[c], rv = u.run_var[c];
-    for (int g = 0; g < rb.groups; ++g) {
-      const double* s = u.stats + (size_t)g * u.gstride;
-      const double mean = s[u.off_sum + c] / u.count;
-      double var = s[u.off_sq + c] / u.count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const double unb = u.ncorr > 1.0 ? var * (u.ncorr / (u.ncorr - 1.0)) : var;
-      rm = (1.f - rb.momentum) * rm + rb.momentum * (float)mean;
-      rv = (1.f - rb.momentum) * rv + rb.momentum * (float)unb;
+    // the recurrence is sequential over the groups (S nn.BatchNorm calls in order), the loads are not: fetch the
+    // sums of 8 groups at a time so that their latencies overlap
+    for (int g0 = 0; g0 < rb.groups; g0 += 8) {
+      double s1[8], s2[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const bool ok = g0 + q < rb.groups;
+        const double* s = u.stats + (size_t)(ok ? g0 + q : g0) * u.gstride;
+        s1[q] = s[u.off_sum + c];
+        s2[q] = s[u.off_sq + c];
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (g0 + q < rb.groups) {
+          const double mean = s1[q] / u.count;
+          double var = s2[q] / u.count - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const double unb = u.ncorr > 1.0 ? var * (u.ncorr / (u.ncorr - 1.0)) : var;
+          rm = (1.f - rb.momentum) * rm + rb.momentum * (float)mean;
+          rv = (1.f - rb.momentum) * rv + rb.momentum * (float)unb;
+        }
+      }
     }
     u.run_mean[c] = rm;
     u.run_var[c] = rv;

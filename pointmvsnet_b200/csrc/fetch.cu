@@ -49,10 +49,12 @@ __device__ void inv3x3(const double* m, double* o) {
 __global__ void cam_setup_kernel(const float* __restrict__ cam_params, const float* __restrict__ interval,
                                  const float* __restrict__ mean, const float* __restrict__ stdv,
                                  float* __restrict__ blocks, int B, int V, float kscale, float iscale) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  // one CTA (32 threads) per batch element: lane v copies / scales view v, lane 0 also inverts the reference
+  // matrices in fp64, the last lane writes the scalars
+  const int b = blockIdx.x;
   if (b >= B) return;
   float* out = blocks + (size_t)b * cam_block_floats(V);
-  for (int v = 0; v < V; ++v) {
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
     const float* ext = cam_params + ((size_t)(b * V + v) * 2 + 0) * 16;
     const float* intr = cam_params + ((size_t)(b * V + v) * 2 + 1) * 16;
     float* o = out + CB_VIEW + v * CB_VSTRIDE;
@@ -79,11 +81,13 @@ __global__ void cam_setup_kernel(const float* __restrict__ cam_params, const flo
       for (int r = 0; r < 3; ++r) out[CB_T0 + r] = ext[r * 4 + 3];
     }
   }
-  for (int r = 0; r < 3; ++r) {
-    out[CB_MEAN + r] = mean ? mean[b * 3 + r] : 0.f;
-    out[CB_STD + r] = stdv ? stdv[b * 3 + r] : 1.f;
+  if (threadIdx.x == blockDim.x - 1) {
+    for (int r = 0; r < 3; ++r) {
+      out[CB_MEAN + r] = mean ? mean[b * 3 + r] : 0.f;
+      out[CB_STD + r] = stdv ? stdv[b * 3 + r] : 1.f;
+    }
+    out[CB_INTERVAL] = interval ? __fmul_rn(iscale, interval[b]) : 0.f;
   }
-  out[CB_INTERVAL] = interval ? __fmul_rn(iscale, interval[b]) : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -212,8 +216,9 @@ struct WarpSourceParams {
   const float* pyr[3];  // channels-last [B*V, hl, wl, 16 << l]
   int hl[3], wl[3];
   float sy[3], sx[3];   // hl / h, wl / w
-  float* out;           // [B*V, h, w, 112]
-  int h, w;
+  float* out;           // [B][V*h*w + 1][112]: the last texel of every batch element is all zeros - the target of
+                        // out-of-image taps (grid_sample's zeros padding, also for non-finite features)
+  int h, w, V;
 };
 
 __global__ void __launch_bounds__(256) warp_source_kernel(const WarpSourceParams p) {
@@ -223,6 +228,10 @@ __global__ void __launch_bounds__(256) warp_source_kernel(const WarpSourceParams
   const int x = xi / FETCH_C4, c4 = xi - x * FETCH_C4;
   const int y = blockIdx.y;
   const long long bv = blockIdx.z;
+  const long long bb = bv / p.V;
+  float* outp = p.out + ((bv * p.h + y) * (long long)p.w * FETCH_C4 + bb * FETCH_C4 + xi) * 4;
+  if (xi < FETCH_C4 && y == 0 && bv - bb * p.V == p.V - 1)  // the batch element's trailing zero texel
+    st4(p.out + ((bb + 1) * ((long long)p.V * p.h * p.w + 1) - 1) * FETCH_CH + xi * 4, make_float4(0.f, 0.f, 0.f, 0.f));
   const int l = c4 < 4 ? 0 : (c4 < 12 ? 1 : 2);
   const int cq = c4 - (l == 0 ? 0 : (l == 1 ? 4 : 12));
   const int C4 = 4 << l;
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(256) warp_source_kernel(const WarpSourceParams
                   __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.z), __fmul_rn(lx1, v11.z))));
   o.w = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.w), __fmul_rn(lx1, v01.w))),
                   __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.w), __fmul_rn(lx1, v11.w))));
-  st4(p.out + ((bv * p.h + y) * (long long)p.w * FETCH_C4 + xi) * 4, o);
+  st4(outp, o);
 }
 
 constexpr int FETCH_WARPS = 8;
@@ -265,8 +274,9 @@ constexpr int FETCH_WARPS = 8;
 struct __align__(16) Desc {
   unsigned o[4];
   float w[4];
+  float wd[4];  // SHARE kernel: w[] and wd[] together hold (w0,w0,w1,w1 | w2,w2,w3,w3) for the packed fp32 FMAs
 };
-static_assert(sizeof(Desc) == 32, "Desc layout");
+static_assert(sizeof(Desc) == 48, "Desc layout");
 
 __host__ __device__ constexpr size_t fetch_smem_bytes(int V) {  // descriptors
   return (size_t)FETCH_WARPS * PMVS_NUM_HYP * V * sizeof(Desc);
@@ -281,7 +291,8 @@ __host__ __device__ constexpr size_t fetch_smem_total(int V) {  // + 16 floats o
 // hypothesis the views are walked in order and the lane keeps the sum / sum of squares of its
 // channels (model.py:188-189), so there is no cross-lane reduction; one tap = one 128-bit
 // ld.global.nc + 4 FFMA per lane, 448 contiguous bytes per warp.
-__global__ void __launch_bounds__(FETCH_WARPS * 32, 4) fused_fetch_kernel(const FusedFetchParams p) {
+template <bool SHARE, int MINB>
+__global__ void __launch_bounds__(FETCH_WARPS * 32, MINB) fused_fetch_kernel(const FusedFetchParams p) {
   __shared__ __align__(16) float cam[cam_block_floats(PMVS_MAX_VIEWS)];
   __shared__ __align__(8) unsigned long long bar;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -329,7 +340,9 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32, 4) fused_fetch_kernel(const 
   const int Npts = PMVS_NUM_HYP * hs * wsub;
   const float rV = __frcp_rn((float)V);
   const size_t fstep = (size_t)hs * wsub * PMVS_FEAT_CH;  // next hypothesis
-  const float4* src = reinterpret_cast<const float4*>(p.src) + (size_t)b * V * h * w * FETCH_C4 + lane;
+  const unsigned zero_tex = (unsigned)(V * h * w) * (unsigned)FETCH_C4;  // the batch element's all-zero texel
+  const float4* src = reinterpret_cast<const float4*>(p.src) + (size_t)b * ((size_t)V * h * w + 1) * FETCH_C4 + lane;
+  // SHARE: bit m*V+v of `eqmask` set <=> hypothesis m hits the same texel quad as hypothesis m-1 in view v
   // (hypothesis, view) pairs this lane describes: t = lane and, for V > 6, lane + 32
   const int m_a = lane / V, v_a = lane - m_a * V;
   const int m_b = (lane + 32) / V, v_b = lane + 32 - m_b * V;
@@ -374,7 +387,8 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32, 4) fused_fetch_kernel(const 
     };
 
     // ---- phase 1: one lane per (hypothesis, view) builds its sampling descriptor --------------
-    for (int t = lane; t < npair; t += 32) {
+    unsigned eqmask = 0u;
+    for (int t = lane; t < (SHARE ? 32 : npair); t += 32) {
       const int m = t < 32 ? m_a : m_b, v = t < 32 ? v_a : v_b;
       float wx, wy, wz;
       world_point(m, wx, wy, wz);
@@ -388,15 +402,26 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32, 4) fused_fetch_kernel(const 
       const unsigned ov = (unsigned)(v * h * w) * (unsigned)FETCH_C4;  // start of the view
       const unsigned o00 = ov + (unsigned)(tp.y0 * w + tp.x0) * (unsigned)FETCH_C4;
       Desc dd;
-      dd.o[0] = k00 ? o00 : ov;
-      dd.o[1] = k01 ? o00 + (unsigned)FETCH_C4 : ov;
-      dd.o[2] = k10 ? o00 + (unsigned)w * (unsigned)FETCH_C4 : ov;
-      dd.o[3] = k11 ? o00 + (unsigned)(w + 1) * (unsigned)FETCH_C4 : ov;
-      dd.w[0] = k00 ? tp.nw : 0.f;
-      dd.w[1] = k01 ? tp.ne : 0.f;
-      dd.w[2] = k10 ? tp.sw : 0.f;
-      dd.w[3] = k11 ? tp.se : 0.f;
-      desc[t] = dd;
+      dd.o[0] = k00 ? o00 : zero_tex;
+      dd.o[1] = k01 ? o00 + (unsigned)FETCH_C4 : zero_tex;
+      dd.o[2] = k10 ? o00 + (unsigned)w * (unsigned)FETCH_C4 : zero_tex;
+      dd.o[3] = k11 ? o00 + (unsigned)(w + 1) * (unsigned)FETCH_C4 : zero_tex;
+      const float w0 = k00 ? tp.nw : 0.f, w1 = k01 ? tp.ne : 0.f, w2 = k10 ? tp.sw : 0.f, w3 = k11 ? tp.se : 0.f;
+      if (SHARE) {
+        dd.w[0] = w0; dd.w[1] = w0; dd.w[2] = w1; dd.w[3] = w1;
+        dd.wd[0] = w2; dd.wd[1] = w2; dd.wd[2] = w3; dd.wd[3] = w3;
+      } else {
+        dd.w[0] = w0; dd.w[1] = w1; dd.w[2] = w2; dd.w[3] = w3;
+        dd.wd[0] = dd.wd[1] = dd.wd[2] = dd.wd[3] = 0.f;
+      }
+      if (!SHARE || t < npair) desc[t] = dd;
+      if (SHARE) {
+        // same texel quad as the PREVIOUS hypothesis of the same view (lane t - V)?  (npair <= 30: all 32 lanes vote)
+        const unsigned q0 = __shfl_up_sync(0xffffffffu, dd.o[0], V), q1 = __shfl_up_sync(0xffffffffu, dd.o[1], V);
+        const unsigned q2 = __shfl_up_sync(0xffffffffu, dd.o[2], V), q3 = __shfl_up_sync(0xffffffffu, dd.o[3], V);
+        eqmask = __ballot_sync(0xffffffffu, t >= V && t < npair && q0 == dd.o[0] && q1 == dd.o[1] && q2 == dd.o[2] &&
+                                                q3 == dd.o[3]);
+      }
     }
     // normalised xyz of the 5 hypothesis points (model.py:46-48,193): lane m computes point m
     if (lane < PMVS_NUM_HYP) {
@@ -413,31 +438,56 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32, 4) fused_fetch_kernel(const 
     const int jj = X - xx * p.ratio;
     const int cloud = (ii * p.ratio + jj) * p.B + b;
     float* frow0 = p.feature + ((size_t)cloud * Npts + (size_t)yy * wsub + xx) * PMVS_FEAT_CH;  // hypothesis 0
+    if (SHARE) {
+      // Views outermost.  Consecutive hypotheses of a pixel project ~0.1 texel apart along the epipolar line, so a
+      // hypothesis usually hits the texel quad of the previous one: the 4 taps are then NOT re-loaded (a warp-uniform
+      // test on the ballot of phase 1), about 1.4 quads per view instead of 5.  The arithmetic is the scalar kernel's
+      // on fp32 pairs (FMUL2 / FFMA2 / FADD2: IEEE rn per lane, so the results are bit-identical); per hypothesis the
+      // views are still accumulated in view order.
+      if (lane < FETCH_C4) {
+        f32x2 s1l[PMVS_NUM_HYP], s1h[PMVS_NUM_HYP], s2l[PMVS_NUM_HYP], s2h[PMVS_NUM_HYP];
+#pragma unroll
+        for (int m = 0; m < PMVS_NUM_HYP; ++m) s1l[m] = s1h[m] = s2l[m] = s2h[m] = pack2(0.f, 0.f);
+#pragma unroll 1
+        for (int v = 0; v < V; ++v) {
+          float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0, t2 = t0, t3 = t0;
+#pragma unroll
+          for (int m = 0; m < PMVS_NUM_HYP; ++m) {
+            const Desc* dm = desc + m * V + v;
+            if (m == 0 || !((eqmask >> (m * V + v)) & 1u)) {  // warp-uniform
+              const uint4 o = *reinterpret_cast<const uint4*>(dm->o);
+              t0 = __ldg(src + o.x); t1 = __ldg(src + o.y); t2 = __ldg(src + o.z); t3 = __ldg(src + o.w);
+            }
+            const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(dm->w);   // (w0,w0) (w1,w1)
+            const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(dm->wd);  // (w2,w2) (w3,w3)
+            // ATen grid_sampler_2d accumulation order: NW, NE, SW, SE
+            const f32x2 al = fma2(pack2(t3.x, t3.y), wb.y, fma2(pack2(t2.x, t2.y), wb.x,
+                                  fma2(pack2(t1.x, t1.y), wa.y, mul2(pack2(t0.x, t0.y), wa.x))));
+            const f32x2 ah = fma2(pack2(t3.z, t3.w), wb.y, fma2(pack2(t2.z, t2.w), wb.x,
+                                  fma2(pack2(t1.z, t1.w), wa.y, mul2(pack2(t0.z, t0.w), wa.x))));
+            // model.py:188-189: sums over views of x and x**2, in view order (square and sum unfused)
+            s1l[m] = add2(s1l[m], al); s1h[m] = add2(s1h[m], ah);
+            s2l[m] = add2(s2l[m], mul2(al, al)); s2h[m] = add2(s2h[m], mul2(ah, ah));
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < PMVS_NUM_HYP; ++m) {
+          float4 s1, s2, o;
+          unpack2(s1l[m], s1.x, s1.y); unpack2(s1h[m], s1.z, s1.w);
+          unpack2(s2l[m], s2.x, s2.y); unpack2(s2h[m], s2.z, s2.w);
+          float a;
+          a = __fmul_rn(s1.x, rV); o.x = __fsub_rn(__fmul_rn(s2.x, rV), __fmul_rn(a, a));
+          a = __fmul_rn(s1.y, rV); o.y = __fsub_rn(__fmul_rn(s2.y, rV), __fmul_rn(a, a));
+          a = __fmul_rn(s1.z, rV); o.z = __fsub_rn(__fmul_rn(s2.z, rV), __fmul_rn(a, a));
+          a = __fmul_rn(s1.w, rV); o.w = __fsub_rn(__fmul_rn(s2.w, rV), __fmul_rn(a, a));
+          st4(frow0 + m * fstep + lane * 4, o);
+        }
+      }
+    } else
     if (lane < FETCH_C4) {
       const Desc* dp = desc;
 #pragma unroll 1
       for (int m = 0; m < PMVS_NUM_HYP; ++m) {
-#if PMVS_F32X2
-        // the same operations on fp32 pairs (FMUL2 / FFMA2 / FADD2): 14 instead of 28 per (m, v)
-        f32x2 s1l = pack2(0.f, 0.f), s1h = s1l, s2l = s1l, s2h = s1l;
-#pragma unroll 2
-        for (int v = 0; v < V; ++v, ++dp) {
-          const Desc dd = *dp;
-          const float4 t0 = __ldg(src + dd.o[0]);
-          const float4 t1 = __ldg(src + dd.o[1]);
-          const float4 t2 = __ldg(src + dd.o[2]);
-          const float4 t3 = __ldg(src + dd.o[3]);
-          const f32x2 w0 = pack2(dd.w[0], dd.w[0]), w1 = pack2(dd.w[1], dd.w[1]);
-          const f32x2 w2 = pack2(dd.w[2], dd.w[2]), w3 = pack2(dd.w[3], dd.w[3]);
-          const f32x2 al = fma2(pack2(t3.x, t3.y), w3, fma2(pack2(t2.x, t2.y), w2, fma2(pack2(t1.x, t1.y), w1, mul2(pack2(t0.x, t0.y), w0))));
-          const f32x2 ah = fma2(pack2(t3.z, t3.w), w3, fma2(pack2(t2.z, t2.w), w2, fma2(pack2(t1.z, t1.w), w1, mul2(pack2(t0.z, t0.w), w0))));
-          s1l = add2(s1l, al); s1h = add2(s1h, ah);
-          s2l = add2(s2l, mul2(al, al)); s2h = add2(s2h, mul2(ah, ah));
-        }
-        float4 s1, s2;
-        unpack2(s1l, s1.x, s1.y); unpack2(s1h, s1.z, s1.w);
-        unpack2(s2l, s2.x, s2.y); unpack2(s2h, s2.z, s2.w);
-#else
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
 #pragma unroll 2
         for (int v = 0; v < V; ++v, ++dp) {
@@ -458,7 +508,6 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32, 4) fused_fetch_kernel(const 
           s2.x = __fadd_rn(s2.x, __fmul_rn(acc.x, acc.x)); s2.y = __fadd_rn(s2.y, __fmul_rn(acc.y, acc.y));
           s2.z = __fadd_rn(s2.z, __fmul_rn(acc.z, acc.z)); s2.w = __fadd_rn(s2.w, __fmul_rn(acc.w, acc.w));
         }
-#endif
         // model.py:190: mean(x^2) - mean(x)^2 (difference unfused); mean = sum * (1/V) as ATen's
         // CUDA mean kernel computes it (identical to sum / V for V a power of two)
         float4 o;
@@ -562,16 +611,17 @@ __global__ void __launch_bounds__(256)
 int launch_cam_setup(const float* cam_params, const float* interval, const float* mean, const float* stdv,
                      float* blocks, int B, int V, float kscale, float iscale, cudaStream_t st) {
   prof_begin("cam_setup", st);
-  cam_setup_kernel<<<cdiv(B, 32), 32, 0, st>>>(cam_params, interval, mean, stdv, blocks, B, V, kscale, iscale);
+  cam_setup_kernel<<<B, 32, 0, st>>>(cam_params, interval, mean, stdv, blocks, B, V, kscale, iscale);
   return check_launch("cam_setup_kernel", st);
 }
 
-int launch_warp_source(const float* const pyr[3], const int hl[3], const int wl[3], float* out, int BV, int h, int w,
-                       cudaStream_t st) {
+int launch_warp_source(const float* const pyr[3], const int hl[3], const int wl[3], float* out, int B, int V, int h,
+                       int w, cudaStream_t st) {
   WarpSourceParams q{};
   for (int l = 0; l < 3; ++l) { q.pyr[l] = pyr[l]; q.hl[l] = hl[l]; q.wl[l] = wl[l]; }
-  q.out = out; q.h = h; q.w = w;
-  PMVS_REQUIRE(BV > 0 && BV <= 65535 && h > 0 && h <= 65535 && w > 0, "warp_source: bad shape");
+  q.out = out; q.h = h; q.w = w; q.V = V;
+  const int BV = B * V;
+  PMVS_REQUIRE(B > 0 && V > 0 && BV <= 65535 && h > 0 && h <= 65535 && w > 0, "warp_source: bad shape");
   for (int l = 0; l < 3; ++l) {
     PMVS_REQUIRE((long long)hl[l] * wl[l] < (1ll << 31), "warp_source: level %d too large", l);
     q.sy[l] = (float)hl[l] / (float)h; q.sx[l] = (float)wl[l] / (float)w;
@@ -582,13 +632,15 @@ int launch_warp_source(const float* const pyr[3], const int hl[3], const int wl[
   return check_launch("warp_source_kernel", st);
 }
 
-size_t warp_source_bytes(int B, int V, int h, int w) { return (size_t)B * V * h * w * FETCH_CH * sizeof(float); }
+size_t warp_source_bytes(int B, int V, int h, int w) {
+  return (size_t)B * ((size_t)V * h * w + 1) * FETCH_CH * sizeof(float);
+}
 
 int launch_fused_fetch(const FusedFetchParams& p0, cudaStream_t st) {
   FusedFetchParams p = p0;
   const long long npix = (long long)p.h * p.w;
   // tap offsets are 32-bit float4 offsets inside one batch element's [V, h, w, 112] map
-  PMVS_REQUIRE(npix * p.V * FETCH_C4 < (1ll << 32), "fused_fetch: V=%d x %dx%d too large", p.V, p.h, p.w);
+  PMVS_REQUIRE((npix * p.V + 1) * FETCH_C4 < (1ll << 32), "fused_fetch: V=%d x %dx%d too large", p.V, p.h, p.w);
   PMVS_REQUIRE(p.h <= 65535 && p.B <= 65535, "fused_fetch: h or B too large");
   p.hs = p.h / p.ratio; p.ws = p.w / p.ratio;
   p.rlog2 = -1;
@@ -599,7 +651,12 @@ int launch_fused_fetch(const FusedFetchParams& p0, cudaStream_t st) {
   dim3 grid(cdiv(p.w, 4 * p.ppw), cdiv(p.h, 2), p.B);  // CTA = (4 * ppw) x 2 pixels
   const size_t smem = fetch_smem_total(p.V);
   prof_begin("fused_fetch", st);
-  fused_fetch_kernel<<<grid, FETCH_WARPS * 32, smem, st>>>(p);
+  if (opt(OPT_FETCH) == 1 && PMVS_NUM_HYP * p.V <= 30)
+    fused_fetch_kernel<true, 3><<<grid, FETCH_WARPS * 32, smem, st>>>(p);
+  else if (opt(OPT_FETCH) == 2 && PMVS_NUM_HYP * p.V <= 30)
+    fused_fetch_kernel<true, 2><<<grid, FETCH_WARPS * 32, smem, st>>>(p);
+  else
+    fused_fetch_kernel<false, 4><<<grid, FETCH_WARPS * 32, smem, st>>>(p);
   return check_launch("fused_fetch_kernel", st);
 }
 

@@ -1,0 +1,533 @@
+// tcgen05 GEMM, second generation: WEIGHTS STATIONARY IN TENSOR MEMORY, points as the N dimension.
+//
+//   Y[r, 0:cout] = f(X[r, 0:K]) * W[0:cout, 0:K]^T       r = points, fp32 in / fp32 out (3xTF32)
+// (reference: the 1x1 nn.Conv1d of networks.py:13-14,22-23,51-52 and nn/conv.py:21-30, followed by
+// train-mode BatchNorm + ReLU, which is fused here as the INPUT transform of the next layer).
+//
+// Why this shape.  The round-1 kernel (gemm_tc.cu) put the points on the M side and both operands in
+// shared memory; every M=128 x N=64 x K=8 MMA then re-read 6 KB of operands at the ~64 B/clk the
+// tensor core's shared-memory port delivers, i.e. the MMAs were operand-fetch bound at 3x their math
+// time, and one CTA per tile serialised load -> convert -> MMA -> epilogue.  Here
+//   * D^T[cout, points] = W[cout, K] * X^T[K, points]: the weight matrix is the A operand and lives in
+//     TENSOR MEMORY for the whole (persistent) kernel - written once per CTA with tcgen05.st, split into
+//     the TF32 planes  [W_hi ; W_lo]  stacked on the M side (cout <= 64) - so a k-step of 128 points
+//     reads only the two 4 KB point planes X_hi, X_lo from shared memory (64 B per point and k-step
+//     instead of 112) and issues 2 MMAs (M=128, N=128, K=8):  [W_hi;W_lo] * X_hi  and  [W_hi;W_lo] * X_lo.
+//     Accumulator lanes [0,64) hold W_hi*X, lanes [64,128) hold W_lo*X; the epilogue adds them.
+//     cout = 128 uses two A operands (W_hi, W_lo) and two accumulators (3 MMAs per k-step).
+//   * warp-specialised, persistent: 8 producer warps (coalesced 128-bit global loads two chunks ahead
+//     in registers -> fused input BatchNorm+ReLU -> TF32 hi/lo split -> K-major SWIZZLE_128B stores
+//     into a 4-stage mbarrier ring), 1 MMA warp (one elected thread: tcgen05.mma, tcgen05.commit frees
+//     the stage), 4 epilogue warps (tcgen05.ld of one accumulator while the MMAs fill the other).
+//   * the accumulator is TRANSPOSED (lane = output channel, column = point): a warp stores 32
+//     consecutive channels of one point = one full 128-byte line per instruction with no shared-memory
+//     staging, and the BatchNorm statistics of the outputs (per-channel sum / sum of squares) are
+//     per-thread running sums - no cross-lane reduction at all; fp64 atomics once per group and CTA.
+// Precision: as gemm_tc.cu - hi = the 10 explicit mantissa bits the tensor core reads, lo = x - hi
+// (exact); the extra W_lo*X_lo term this formulation adds is below fp32 resolution.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace pmvs {
+
+namespace ws {
+
+constexpr int NT = 128;                       // points per tile == UMMA N
+constexpr int KC = 32;                        // fp32 K columns per chunk == one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int PLANE_BYTES = NT * KC * 4;      // 16 KB
+constexpr int STAGE_BYTES = 2 * PLANE_BYTES;  // X_hi, X_lo
+constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
+constexpr int MMA_WARP = EPI_WARPS;           // warp 4
+constexpr int PROD_WARP0 = EPI_WARPS + 1;     // warps 5..12
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int THREADS = 32 * (EPI_WARPS + 1 + PROD_WARPS);  // 416
+constexpr int XPITCH = 36;                    // floats per accumulator-lane row of the epilogue staging buffer
+constexpr int XBUF_BYTES = 128 * XPITCH * 4;  // 18 432 B: 128 lanes x 32 points (+ pad) of one accumulator slab
+constexpr int PF = 4;                         // chunks of global loads in flight per producer thread
+constexpr int MAXK = 224;
+constexpr int A_LD = NT * 8 / PROD_THREADS;   // float4 loads per producer thread and chunk (4)
+
+constexpr int SM_RING = 0;
+constexpr int SM_XBUF = SM_RING + STAGES * STAGE_BYTES;
+constexpr int SM_BN = SM_XBUF + 2 * XBUF_BYTES;
+constexpr int SM_BAR = SM_BN + 4 * MAXK * 4;
+constexpr int SM_TOTAL = SM_BAR + 128 + 1024 /* alignment slack */;
+
+constexpr int TM_A = 0;      // A operand(s): columns [0, 256)
+constexpr int TM_A2 = 128;   // second A operand (W_lo) when cout = 128
+constexpr int TM_D = 256;    // accumulators: two 128-column buffers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (see gemm_tc.cu make_desc)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+struct TileRange {
+  int first, count;
+};
+__device__ __forceinline__ TileRange my_tiles(int total) {
+  // contiguous, balanced: CTA b owns [b*total/G, (b+1)*total/G)
+  const long long G = gridDim.x, b = blockIdx.x;
+  const int lo = (int)(b * total / G), hi = (int)((b + 1) * total / G);
+  return TileRange{lo, hi - lo};
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
+  constexpr bool STACKED = COUT <= 64;
+  constexpr int ACC_BUFS = STACKED ? 2 : 1;
+  extern __shared__ unsigned char ws_smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)ws_smem_raw + 1023) & ~(uintptr_t)1023);
+  float* sBN = (float*)(smem + SM_BN);  // mean, istd, gamma, beta x MAXK
+  uint64_t* bars = (uint64_t*)(smem + SM_BAR);
+  // bars: full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]; then the TMEM base slot
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (uint32_t)(STAGES + s); };
+  auto bar_accf = [&](int b) { return bar0 + 8u * (uint32_t)(2 * STAGES + b); };
+  auto bar_acce = [&](int b) { return bar0 + 8u * (uint32_t)(2 * STAGES + 2 + b); };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+  const int K = a.cin;
+  const int nch = (K + KC - 1) / KC;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tpg = (a.rows_per_group + NT - 1) / NT;  // tiles per group
+  const TileRange tr = my_tiles(a.groups * tpg);
+  const bool in_bn = a.in_stats != nullptr;
+
+  if (warp == MMA_WARP) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(bar_full(s), PROD_WARPS);
+        mbar_init(bar_empty(s), 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_accf(b), 1);
+        mbar_init(bar_acce(b), EPI_WARPS);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < EPI_WARPS) {
+    // ---- weights -> tensor memory (A operand): lane L of TMEM = row L of [W_hi ; W_lo] ----------------
+    const int L = warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (STACKED) {
+      const bool is_hi = L < COUT, is_lo = L >= 64 && L < 64 + COUT;
+      const float* wrow = a.w + (size_t)(is_hi ? L : (is_lo ? L - 64 : 0)) * K;
+      for (int k0 = 0; k0 < K; k0 += 8) {
+        float v[8];
+        const float4 w0 = ldg4(wrow + k0), w1 = ldg4(wrow + k0 + 4);
+        const float x[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float h = tf32_hi(x[i]);
+          v[i] = is_hi ? h : (is_lo ? __fsub_rn(x[i], h) : 0.f);
+        }
+        tmem_st8(lane_addr + TM_A + k0, v);
+      }
+    } else {
+      const float* wrow = a.w + (size_t)L * K;
+      for (int k0 = 0; k0 < K; k0 += 8) {
+        float vh[8], vl[8];
+        const float4 w0 = ldg4(wrow + k0), w1 = ldg4(wrow + k0 + 4);
+        const float x[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          vh[i] = tf32_hi(x[i]);
+          vl[i] = __fsub_rn(x[i], vh[i]);
+        }
+        tmem_st8(lane_addr + TM_A + k0, vh);
+        tmem_st8(lane_addr + TM_A2 + k0, vl);
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp >= PROD_WARP0) {
+    // =============================== producers ==========================================================
+    const int ptid = tid - PROD_WARP0 * 32;
+    const int pc = ptid & 7;    // 16-byte piece inside the 128-byte row
+    const int prow = ptid >> 3;  // 0..31 ; rows prow + 32*i
+    const int total = tr.count * nch;
+    int cur_g = -1;
+    float4 buf[PF + 1][A_LD];
+
+    // (tile, chunk) cursors of the load stream and of the store stream: both walk items 0, 1, 2, .. in order, so
+    // they advance incrementally (no integer divisions on the per-chunk path)
+    struct Cursor {
+      int g, row0, c;
+    };
+    Cursor ci, cp;
+    {
+      const int t0 = tr.first;
+      ci.g = t0 / tpg; ci.row0 = (t0 - ci.g * tpg) * NT; ci.c = 0;
+      cp = ci;
+    }
+    auto advance = [&](Cursor& cu) {
+      if (++cu.c == nch) {
+        cu.c = 0;
+        cu.row0 += NT;
+        if (cu.row0 >= a.rows_per_group) {
+          cu.row0 = 0;
+          ++cu.g;
+        }
+      }
+    };
+    auto issue = [&](float4 (&xa)[A_LD]) {
+      const int rows_valid = min(NT, a.rows_per_group - ci.row0);
+      const float* xrow = a.x + ((size_t)ci.g * a.rows_per_group + ci.row0 + prow) * a.ldx + ci.c * KC + pc * 4;
+      const bool kvalid = ci.c * KC + pc * 4 < K;
+#pragma unroll
+      for (int i = 0; i < A_LD; ++i) {
+        const int r = prow + 32 * i;
+        xa[i] = (kvalid && r < rows_valid) ? ldg4(xrow + (size_t)(32 * i) * a.ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      advance(ci);
+    };
+    auto put = [&](const float4 (&xa)[A_LD], int n) {
+      const int g = cp.g, c = cp.c;
+      const int rows_valid = min(NT, a.rows_per_group - cp.row0);
+      if (in_bn && g != cur_g) {  // uniform over all producer threads: they walk the same item sequence
+        named_bar_sync(1, PROD_THREADS);
+        const double* s = a.in_stats + (size_t)g * 2 * K;
+        for (int cc = ptid; cc < K; cc += PROD_THREADS) {
+          const BnCoef k = bn_coef(s[cc], s[K + cc], a.in_count, a.eps);
+          sBN[cc] = k.mean;
+          sBN[MAXK + cc] = k.invstd;
+          sBN[2 * MAXK + cc] = a.in_gamma[cc];
+          sBN[3 * MAXK + cc] = a.in_beta[cc];
+        }
+        named_bar_sync(1, PROD_THREADS);
+        cur_g = g;
+      }
+      const int stage = n % STAGES;
+      mbar_wait(bar_empty(stage), (uint32_t)(((n / STAGES) & 1) ^ 1));
+      unsigned char* hi_plane = smem + SM_RING + stage * STAGE_BYTES;
+      const int k0 = c * KC + pc * 4;
+      const bool kvalid = k0 < K;
+#pragma unroll
+      for (int i = 0; i < A_LD; ++i) {
+        const int r = prow + 32 * i;
+        float4 v = xa[i];
+        if (in_bn && kvalid && r < rows_valid) {
+          v.x = fmaxf(bn_apply(v.x, sBN[k0 + 0], sBN[MAXK + k0 + 0], sBN[2 * MAXK + k0 + 0], sBN[3 * MAXK + k0 + 0]), 0.f);
+          v.y = fmaxf(bn_apply(v.y, sBN[k0 + 1], sBN[MAXK + k0 + 1], sBN[2 * MAXK + k0 + 1], sBN[3 * MAXK + k0 + 1]), 0.f);
+          v.z = fmaxf(bn_apply(v.z, sBN[k0 + 2], sBN[MAXK + k0 + 2], sBN[2 * MAXK + k0 + 2], sBN[3 * MAXK + k0 + 2]), 0.f);
+          v.w = fmaxf(bn_apply(v.w, sBN[k0 + 3], sBN[MAXK + k0 + 3], sBN[2 * MAXK + k0 + 3], sBN[3 * MAXK + k0 + 3]), 0.f);
+        }
+        const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((pc ^ (r & 7)) << 4);
+        float4 hi, lo;
+        hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+        lo.x = __fsub_rn(v.x, hi.x); lo.y = __fsub_rn(v.y, hi.y); lo.z = __fsub_rn(v.z, hi.z); lo.w = __fsub_rn(v.w, hi.w);
+        *reinterpret_cast<float4*>(hi_plane + off) = hi;
+        *reinterpret_cast<float4*>(hi_plane + PLANE_BYTES + off) = lo;
+      }
+      // No fence.proxy.async here: it lowers to MEMBAR.ALL.CTA, which would wait for this thread's PF chunks of
+      // global loads in flight and serialise the prefetch.  The stores are published by the release-arrive below;
+      // the MMA thread executes the proxy fence after its acquire-wait, before it issues the MMAs that read them.
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full(stage));
+      advance(cp);
+    };
+
+    // PF chunks (PF x 16 KB per SM) of loads in flight while one is converted and stored: at ~1.5 us of loaded
+    // DRAM latency the SM's share of the HBM bandwidth needs ~50 KB in flight
+#pragma unroll
+    for (int i = 0; i < PF; ++i)
+      if (i < total) issue(buf[i]);
+    for (int n = 0; n < total; n += PF + 1) {
+#pragma unroll
+      for (int u = 0; u <= PF; ++u) {
+        const int m = n + u;
+        if (m < total) {
+          if (m + PF < total) issue(buf[(u + PF) % (PF + 1)]);
+          put(buf[u], m);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // =============================== MMA issuer ==========================================================
+    // the whole warp walks the pipeline (converged waits); lane 0 issues the MMAs and commits
+    {
+      constexpr uint32_t idesc = make_idesc(128, NT);
+      int n = 0;
+      for (int it = 0; it < tr.count; ++it) {
+        const int b = STACKED ? (it & 1) : 0;
+        const int use = STACKED ? (it >> 1) : it;
+        mbar_wait(bar_acce(b), (uint32_t)((use & 1) ^ 1));  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + TM_D + (STACKED ? b * NT : 0);
+        for (int c = 0; c < nch; ++c, ++n) {
+          const int stage = n % STAGES;
+          mbar_wait(bar_full(stage), (uint32_t)((n / STAGES) & 1));
+          fence_proxy_async();  // the producers' generic-proxy stores (acquired above) -> the tensor core's async proxy
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t x_hi = smem_u32(smem + SM_RING + stage * STAGE_BYTES), x_lo = x_hi + PLANE_BYTES;
+            const int ksteps = min(KC, K - c * KC) / 8;
+            for (int j = 0; j < ksteps; ++j) {
+              const uint32_t acc = (c == 0 && j == 0) ? 0u : 1u;
+              const uint32_t ka = (uint32_t)(c * KC + j * 8);
+              if (STACKED) {
+                umma_tf32_ts(d0, tmem_base + TM_A + ka, make_desc(x_hi + j * 32), idesc, acc);
+                umma_tf32_ts(d0, tmem_base + TM_A + ka, make_desc(x_lo + j * 32), idesc, 1u);
+              } else {
+                umma_tf32_ts(d0, tmem_base + TM_A + ka, make_desc(x_hi + j * 32), idesc, acc);
+                umma_tf32_ts(d0, tmem_base + TM_A + ka, make_desc(x_lo + j * 32), idesc, 1u);
+                umma_tf32_ts(d0 + NT, tmem_base + TM_A2 + ka, make_desc(x_hi + j * 32), idesc, acc);
+              }
+            }
+            umma_commit(bar_empty(stage));  // the MMAs have consumed this stage's shared memory
+            if (c == nch - 1) umma_commit(bar_accf(b));  // accumulator complete
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue ===========================================================
+    const int q = warp;  // TMEM lane quarter
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* const xs = (float*)(smem + SM_XBUF);  // 2 x [128 lanes][XPITCH]
+    // stacked: accumulator lanes [0,64) = W_hi * X, [64,128) = W_lo * X of channels [0,64).  A slab (32 points) of
+    // all 128 lanes goes through shared memory; afterwards warp q adds the halves of points [8q, 8q+8) for the
+    // channels `lane` and `lane + 32` and stores them (32 consecutive channels of a point = one 128-byte line).
+    constexpr int NCH_T = STACKED ? 2 : 1;   // channels per thread
+    const int chs[2] = {STACKED ? lane : q * 32 + lane, lane + 32};
+    double acc1[NCH_T], acc2[NCH_T];
+#pragma unroll
+    for (int h = 0; h < NCH_T; ++h) acc1[h] = acc2[h] = 0.0;
+    int acc_g = -1;
+    auto flush = [&]() {
+      if (a.out_stats != nullptr && acc_g >= 0) {
+        double* o = a.out_stats + (size_t)acc_g * 2 * a.cout;
+#pragma unroll
+        for (int h = 0; h < NCH_T; ++h) {
+          if (chs[h] < COUT) {
+            atomicAdd(o + chs[h], acc1[h]);
+            atomicAdd(o + a.cout + chs[h], acc2[h]);
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < NCH_T; ++h) acc1[h] = acc2[h] = 0.0;
+    };
+    for (int it = 0; it < tr.count; ++it) {
+      const int t = tr.first + it;
+      const int g = t / tpg, row0 = (t - g * tpg) * NT;
+      const int rows_valid = min(NT, a.rows_per_group - row0);
+      const size_t grow0 = (size_t)g * a.rows_per_group + row0;
+      if (g != acc_g) {
+        flush();
+        acc_g = g;
+      }
+      const int b = STACKED ? (it & 1) : 0;
+      const int use = STACKED ? (it >> 1) : it;
+      mbar_wait(bar_accf(b), (uint32_t)(use & 1));
+      tc_fence_after();
+      const uint32_t d0 = lane_addr + TM_D + (STACKED ? b * NT : 0);
+      float s1[NCH_T], s2[NCH_T];
+#pragma unroll
+      for (int h = 0; h < NCH_T; ++h) s1[h] = s2[h] = 0.f;
+#pragma unroll 1
+      for (int slab = 0; slab < NT / 32; ++slab) {
+        float v[32];
+        tmem_ld32(d0 + slab * 32, v);
+        if (STACKED) {
+          float* xb = xs + (slab & 1) * (XBUF_BYTES / 4);
+          float* xrow = xb + (q * 32 + lane) * XPITCH;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(xrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          named_bar_sync(2 + (slab & 1), EPI_WARPS * 32);
+          const int p0 = slab * 32 + q * 8;  // first of this warp's 8 points of the slab
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ch = chs[h];
+            const float* hi = xb + ch * XPITCH + q * 8;
+            const float* lo = hi + 64 * XPITCH;
+            const float4 h0 = *reinterpret_cast<const float4*>(hi), h1 = *reinterpret_cast<const float4*>(hi + 4);
+            const float4 l0 = *reinterpret_cast<const float4*>(lo), l1 = *reinterpret_cast<const float4*>(lo + 4);
+            const float o[8] = {h0.x + l0.x, h0.y + l0.y, h0.z + l0.z, h0.w + l0.w,
+                                h1.x + l1.x, h1.y + l1.y, h1.z + l1.z, h1.w + l1.w};
+            if (ch < COUT) {
+              float* yp = a.y + (grow0 + p0) * a.ldy + ch;
+              if (p0 + 8 <= rows_valid) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  *yp = o[i];
+                  yp += a.ldy;
+                  s1[h] += o[i];
+                  s2[h] = fmaf(o[i], o[i], s2[h]);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (p0 + i < rows_valid) {
+                    yp[(size_t)i * a.ldy] = o[i];
+                    s1[h] += o[i];
+                    s2[h] = fmaf(o[i], o[i], s2[h]);
+                  }
+                }
+              }
+            }
+          }
+        } else {
+          float v2[32];
+          tmem_ld32(d0 + NT + slab * 32, v2);
+          const int ch = chs[0];
+          float* yp = a.y + (grow0 + slab * 32) * a.ldy + ch;
+          if (slab * 32 + 32 <= rows_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float o = v[j] + v2[j];
+              *yp = o;
+              yp += a.ldy;
+              s1[0] += o;
+              s2[0] = fmaf(o, o, s2[0]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (slab * 32 + j < rows_valid) {
+                const float o = v[j] + v2[j];
+                yp[(size_t)j * a.ldy] = o;
+                s1[0] += o;
+                s2[0] = fmaf(o, o, s2[0]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce(b));
+#pragma unroll
+      for (int h = 0; h < NCH_T; ++h) {
+        acc1[h] += (double)s1[h];
+        acc2[h] += (double)s2[h];
+      }
+    }
+    flush();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+template <int COUT>
+static int launch_one(const GemmArgs& a, cudaStream_t st, const char* name) {
+  static unsigned long long smem_done = 0;
+  PMVS_TRY(ensure_dyn_smem(gemm_ws_kernel<COUT>, SM_TOTAL, smem_done, "gemm_ws"));
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  const long long tiles = (long long)a.groups * cdiv(a.rows_per_group, NT);
+  const int grid = (int)std::min<long long>(tiles, num_sms);
+  prof_begin(name, st);
+  gemm_ws_kernel<COUT><<<grid, THREADS, SM_TOTAL, st>>>(a);
+  return check_launch("gemm_ws_kernel", st);
+}
+
+}  // namespace ws
+
+// returns -1 when this path does not apply (caller falls back to gemm_tc / SIMT)
+int launch_gemm_ws(const GemmArgs& a, cudaStream_t st, const char* name) {
+  if (a.cin % 8 != 0 || a.cin > ws::MAXK || a.ldx % 4 != 0 || a.groups <= 0 || a.rows_per_group <= 0) return -1;
+  if (((uintptr_t)a.x & 15) || ((uintptr_t)a.w & 15)) return -1;
+  if ((long long)a.groups * cdiv(a.rows_per_group, ws::NT) >= (1ll << 31) / ws::MAXK) return -1;
+  switch (a.cout) {
+    case 16: return ws::launch_one<16>(a, st, name);
+    case 32: return ws::launch_one<32>(a, st, name);
+    case 64: return ws::launch_one<64>(a, st, name);
+    case 128: return a.cin <= 128 ? ws::launch_one<128>(a, st, name) : -1;
+  }
+  return -1;
+}
+
+}  // namespace pmvs

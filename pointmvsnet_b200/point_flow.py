@@ -1,6 +1,9 @@
 """PointFlow: the ``point_flow`` closure of the reference (pointmvsnet/model.py:150-295)
 as an nn.Module, executed by libpmvs_b200.so.
 
+FORWARD ONLY (inference, as test.py runs it: under torch.no_grad() with the module in train() mode so that
+BatchNorm uses batch statistics); calling it with autograd enabled on trainable parameters raises.
+
 One call = one refinement iteration = ~16 kernel launches enqueued by a single C-ABI
 call (``pmvs_point_flow_iter``); ``PointFlowPass`` runs the reference's iteration loop
 (model.py:297-303) and can capture it into a CUDA graph.
@@ -85,9 +88,26 @@ class PointFlow(nn.Module):
         self._wcache = None
         return self
 
+    def _bn_hyper(self):
+        """(momentum, eps) shared by the six BatchNorm layers of the path.  The fused kernels take ONE pair
+        (the reference builds every layer with the defaults, nn/conv.py:17,24, networks.py:16), so differing
+        values are an error here instead of being silently ignored; momentum=None (cumulative average) is not
+        implemented by the fused running-statistics update."""
+        bns = self._bn_modules()
+        mom, eps = bns[0].momentum, bns[0].eps
+        for bn in bns:
+            if bn.momentum != mom or bn.eps != eps:
+                raise NotImplementedError("PointFlow: all BatchNorm layers must share momentum and eps "
+                                          "(got %r/%r and %r/%r)" % (mom, eps, bn.momentum, bn.eps))
+        if mom is None:
+            raise NotImplementedError("PointFlow: BatchNorm momentum=None (cumulative moving average) is not supported "
+                                      "by the fused path")
+        return float(mom), float(eps)
+
     def _weights(self, device):
         # running statistics are passed by pointer on every call and are not part of the key
-        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        mom, eps = self._bn_hyper()
+        key = (str(device), mom, eps) + tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._wcache is not None and self._wcache[0] == key:
             return self._wcache[1], self._wcache[2]
         keep = []
@@ -109,8 +129,8 @@ class PointFlow(nn.Module):
             w.mlp_gamma[l] = ptr(dev(mlp[l].bn.weight))
             w.mlp_beta[l] = ptr(dev(mlp[l].bn.bias))
         w.mlp_w[3] = ptr(dev(self.flow_mlp[1].weight.detach()[:, :, 0]))
-        w.momentum = float(self.flow_edge_conv[0].bn.momentum if self.flow_edge_conv[0].bn.momentum is not None else 0.1)
-        w.eps = float(self.flow_edge_conv[0].bn.eps)
+        w.momentum = mom
+        w.eps = eps
         self._wcache = (key, w, keep)
         return w, keep
 
@@ -182,6 +202,12 @@ class PointFlow(nn.Module):
             # available through the stand-alone EdgeConv modules.
             raise NotImplementedError("PointFlow implements the reference's inference mode (module.train(), "
                                       "batch-statistics BatchNorm, test.py:58); call .train() on it")
+        if torch.is_grad_enabled() and (estimated_depth_map.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
+            # Forward only: the fused path has no backward, so a training loop would run and silently never
+            # update flow_edge_conv / flow_mlp.  Inference runs under torch.no_grad() (test.py:62).
+            raise NotImplementedError("pointmvsnet_b200 PointFlow is forward-only; wrap the call in torch.no_grad() "
+                                      "(training the flow modules needs the stand-alone operators)")
         dev = estimated_depth_map.device
         if pyramids_channels_last is None:
             pyramids_channels_last = self.pyramids_to_channels_last(feature_pyramids)
@@ -191,6 +217,7 @@ class PointFlow(nn.Module):
         if img_hw is None:
             img_hw = (pyr_hw[0][0] * 2, pyr_hw[0][1] * 2)  # conv1 is at half resolution (networks.py:84-124)
         depth = _lib.f32c(estimated_depth_map)
+        self._validate(dev, B, V, pyr, depth, interval, mean, std, cam_params_list)
         shape = self.make_shape(B, V, pyr_hw, tuple(depth.shape[2:]), img_hw, image_scale, is_test, interval_scale)
         ws, need = self._workspace(shape, dev)
         w, _keep = self._weights(dev)
@@ -209,6 +236,9 @@ class PointFlow(nn.Module):
             prob_out = torch.empty(B, 5, h, wd, device=dev, dtype=torch.float32)
         else:
             depth_out, prob_out = out
+            for t, shp in ((depth_out, (B, 1, h, wd)), (prob_out, (B, 5, h, wd))):
+                if tuple(t.shape) != shp or t.dtype != torch.float32 or t.device != dev or not t.is_contiguous():
+                    raise RuntimeError("PointFlow: `out` tensors must be contiguous fp32 %s on %s" % (shp, dev))
         cams = _lib.f32c(cam_params_list)
         itv = _lib.f32c(interval.reshape(-1))
         mean_c, std_c = _lib.f32c(mean), _lib.f32c(std)
@@ -220,13 +250,41 @@ class PointFlow(nn.Module):
         self._last = (shape, ws)
         return depth_out, prob_out
 
+    def _validate(self, dev, B, V, pyr, depth, interval, mean, std, cams):
+        """The C ABI takes raw pointers: everything it will dereference is checked here (device, dtype, sizes)
+        so that a mismatch is a RuntimeError and not an out-of-bounds device access."""
+        for name, t in (("interval", interval), ("mean", mean), ("std", std), ("cam_params_list", cams)):
+            if t.device != dev:
+                raise RuntimeError("PointFlow: %s is on %s, the depth map on %s" % (name, t.device, dev))
+        if tuple(cams.shape[2:]) != (2, 4, 4):
+            raise RuntimeError("PointFlow: cam_params_list must be [B,V,2,4,4], got %s" % (tuple(cams.shape),))
+        if interval.numel() != B:
+            raise RuntimeError("PointFlow: interval has %d elements for batch %d" % (interval.numel(), B))
+        if tuple(mean.shape) != (B, 3) or tuple(std.shape) != (B, 3):
+            raise RuntimeError("PointFlow: mean / std must be [B,3]")
+        if depth.dim() != 4 or depth.shape[0] != B or depth.shape[1] != 1:
+            raise RuntimeError("PointFlow: depth map must be [B,1,h,w] with B=%d, got %s" % (B, tuple(depth.shape)))
+        for l, t in enumerate(pyr):
+            if t.device != dev or t.dtype != torch.float32 or tuple(t.shape[:2]) != (B, V) or t.shape[-1] != PYR_CH[l]:
+                raise RuntimeError("PointFlow: pyramid level %d must be fp32 [B=%d,V=%d,h,w,%d] (channels last) on %s, "
+                                   "got %s on %s" % (l, B, V, PYR_CH[l], dev, tuple(t.shape), t.device))
+        for bn in self._bn_modules():
+            for name in ("running_mean", "running_var", "num_batches_tracked"):
+                buf = getattr(bn, name)
+                if buf is not None and buf.device != dev:
+                    raise RuntimeError("PointFlow: module buffers live on %s, inputs on %s (call .to(device))"
+                                       % (buf.device, dev))
+            if bn.running_mean is not None and (bn.running_mean.dtype != torch.float32 or
+                                                bn.num_batches_tracked.dtype != torch.int64):
+                raise RuntimeError("PointFlow: BatchNorm buffers must be fp32 / int64")
+
     # ------------------------------------------------------------------ debugging / parity
     def debug_stages(self):
         """Views of the last iteration's workspace in the REFERENCE layouts (test helper):
         feature [B,136,5,h,w]-equivalent per sub-cloud etc.  Returns a dict of tensors
         indexed [S, B, ...]."""
         shape, ws = self._last
-        off = (C.c_size_t * 8)()
+        off = (C.c_size_t * 10)()
         check(lib.pmvs_point_flow_debug_offsets(C.byref(shape), C.byref(off)))
         S = shape.ratio * shape.ratio
         hs, wsub = shape.flow_h // shape.ratio, shape.flow_w // shape.ratio
@@ -237,9 +295,18 @@ class PointFlow(nn.Module):
             nbytes = R * cols * 4
             return ws[o:o + nbytes].view(dtype).view(S, shape.B, N, cols)
 
+        cand = ws[off[8]:off[8] + R * 16].view(S, shape.B, N, 16)
+        if off[9]:
+            idx = view(off[2], 16, torch.int32)
+        else:
+            # the tile EdgeConv path keeps 1-byte candidate ids only (d*25 + h*5 + w, bit 7 = outside the
+            # grid); the reference's linear index is n + dd*HW + dh*W + dw clamped (torch_utils.py:51-59)
+            j = (cand & 127).to(torch.int64)
+            n = torch.arange(N, device=ws.device).view(1, 1, N, 1)
+            idx = (n + (j // 25 - 2) * (hs * wsub) + ((j % 25) // 5 - 2) * wsub + (j % 5 - 2)).clamp_(0, N - 1).int()
         return {
             "feature": view(off[0], 136), "xyz": ws[off[1]:off[1] + R * 12].view(torch.float32).view(S, shape.B, 3, N),
-            "idx": view(off[2], 16, torch.int32), "edge": view(off[3], 224), "h2": view(off[4], 16),
+            "idx": idx, "cand": cand, "edge": view(off[3], 224), "h2": view(off[4], 16),
             "S": S, "hs": hs, "ws": wsub, "N": N,
         }
 

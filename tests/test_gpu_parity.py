@@ -435,6 +435,48 @@ def test_linear_pm_modes_vs_fp64(mode, rtol, cin, cout, rows):
     assert torch.allclose(out_stats[cout:], (want * want).sum(0), rtol=2 * srt + 1e-4)
 
 
+@pytest.mark.parametrize("gemm_opt", [0, 1])
+@pytest.mark.parametrize("cin,cout,groups,rows", [(64, 64, 3, 1000), (136, 64, 2, 25600), (64, 128, 5, 333),
+                                                  (64, 16, 4, 4097), (32, 64, 16, 640), (224, 64, 2, 129)])
+def test_linear_pm_groups_ragged_tiles_both_tcgen05_kernels(gemm_opt, cin, cout, groups, rows):
+    """Several BatchNorm groups per launch (per-group input statistics, per-group output sums), row counts that
+    are not multiples of the 128-point tile, for both tensor-core kernels (gemm_tc.cu / gemm_ws.cu), 3xTF32."""
+    from pointmvsnet_b200 import _lib
+    gen = torch.Generator().manual_seed(cin * 7 + cout + groups)
+    x = (torch.randn(groups, rows, cin, generator=gen) * (1 + torch.arange(groups).view(-1, 1, 1))).to(DEV)
+    w = (torch.randn(cout, cin, generator=gen) / cin ** 0.5).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(cin, generator=gen)).to(DEV)
+    beta = (0.1 * torch.randn(cin, generator=gen)).to(DEV)
+    xs = x.double()
+    in_stats = torch.cat([xs.sum(1), (xs * xs).sum(1)], dim=1).contiguous()  # [groups, 2*cin]
+    y = torch.full((groups, rows, cout), float("nan"), device=DEV)
+    out_stats = torch.zeros(groups, 2 * cout, device=DEV, dtype=torch.float64)
+    old = _lib.get_option("gemm")
+    try:
+        _lib.set_option("gemm", gemm_opt)
+        for use_bn in (True, False):
+            out_stats.zero_()
+            _lib.check(_lib.lib.pmvs_linear_pm(x.data_ptr(), cin, w.data_ptr(), y.data_ptr(), cout, groups, rows, cin,
+                                               cout, in_stats.data_ptr() if use_bn else None,
+                                               gamma.data_ptr() if use_bn else None, beta.data_ptr() if use_bn else None,
+                                               float(rows), 1e-5, out_stats.data_ptr(), _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            if use_bn:
+                mean = xs.mean(1, keepdim=True)
+                var = xs.var(1, unbiased=False, keepdim=True)
+                xn = torch.relu((xs - mean) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double())
+            else:
+                xn = xs
+            want = xn @ w.double().t()
+            scale = (xn.abs() @ w.double().abs().t()).clamp(min=1e-6)
+            err = ((y.double() - want).abs() / scale).max().item()
+            assert err < 1e-5, (gemm_opt, use_bn, cin, cout, err)
+            assert torch.allclose(out_stats[:, :cout], want.sum(1), rtol=1e-4, atol=1e-4 * scale.sum(1).max().item())
+            assert torch.allclose(out_stats[:, cout:], (want * want).sum(1), rtol=3e-4)
+    finally:
+        _lib.set_option("gemm", old)
+
+
 def test_ragged_shapes_six_views_vs_oracle(golden_params, golden_weights):
     """A C5-like shape in miniature: sub-grid 37 x 50 (odd, not a multiple of any tile), 6 views
     (the shared-memory opt-in path of the fetch kernel), iterations 1 and 2, all stages vs oracle."""
@@ -448,6 +490,45 @@ def test_ragged_shapes_six_views_vs_oracle(golden_params, golden_weights):
         assert torch.allclose(d_gpu, res, atol=5e-4, rtol=0), (it, (d_gpu - res).abs().max())
         assert torch.allclose(p_gpu, prob, atol=5e-5, rtol=0)
         depth = res
+
+
+@pytest.mark.parametrize("views", [7, 12])
+def test_point_flow_many_views_second_descriptor_pass(views, golden_params, golden_weights):
+    """V > 6: more than 32 (hypothesis, view) pairs per pixel, i.e. the second descriptor pass of the fetch
+    kernel (lane + 32), up to PMVS_MAX_VIEWS = 12."""
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    cpu = make_pointflow_inputs(64, 128, views, 1, 48, seed=30 + views)
+    pf = _pf(golden_weights)
+    res, prob, stg, d_gpu, p_gpu = _run_iteration(pf, cpu, cpu["coarse_depth"], 0.25, 0.75, 1, golden_params)
+    _check_stages(pf, stg, 1)
+    assert torch.allclose(d_gpu, res, atol=5e-4, rtol=0)
+    assert torch.allclose(p_gpu, prob, atol=5e-5, rtol=0)
+
+
+def test_fetch_zero_padding_with_non_finite_features(golden_params, golden_weights):
+    """grid_sample's zeros padding yields exact zeros for out-of-image taps whatever the map holds; the fused
+    fetch points such taps at an all-zero texel instead of weighting a real texel by 0 (0 * inf = nan)."""
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    cpu = make_pointflow_inputs(64, 128, 3, 1, 48, seed=41)
+    # push the source cameras sideways so that many projections leave the image, and poison texel (0, 0)
+    cpu["cam_params_list"][:, 1:, 0, 0, 3] += 120.0
+    for lvl in cpu["pyramids"]:
+        lvl[:, :, :, 0, 0] = float("inf")
+    pf = _pf(golden_weights)
+    with torch.no_grad():
+        stg_feature, _, _ = O.build_point_features(cpu["coarse_depth"], 0.75 * cpu["depth_interval"], 0.25,
+                                                   cpu["pyramids"], cpu["cam_params_list"], cpu["mean"], cpu["std"],
+                                                   cpu["img_hw"])
+        pf(cpu["coarse_depth"].to(DEV), (0.75 * cpu["depth_interval"]).to(DEV), 0.25, 1,
+           feature_pyramids=[p.to(DEV) for p in cpu["pyramids"]], cam_params_list=cpu["cam_params_list"].to(DEV),
+           mean=cpu["mean"].to(DEV), std=cpu["std"].to(DEV), img_hw=cpu["img_hw"])
+    dbg = pf.debug_stages()
+    feat = sub_to_ref(dbg["feature"].cpu(), dbg["S"], 1, 5, dbg["hs"], dbg["ws"], 2)[:, :112]
+    want = stg_feature[:, :112]
+    finite = torch.isfinite(want)
+    assert finite.float().mean() > 0.9 and (~finite).any()
+    assert torch.equal(torch.isfinite(feat), finite)
+    assert torch.allclose(feat[finite], want[finite], atol=3e-5, rtol=1e-5)
 
 
 def test_coarse_cost_volume_golden_and_oracle():

@@ -17,7 +17,7 @@ if [[ "${1:-}" == *.so ]]; then
 else
   bash pointmvsnet_b200/csrc/build.sh "$@" > "gpurun_out/build_${tag}.log" 2>&1 || { tail -20 "gpurun_out/build_${tag}.log"; exit 1; }
 fi
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 900 python -m pytest ${PMVS_TESTS:-tests} -m gpu -x -q 2>&1 | tail -5
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > "gpurun_out/bench_${tag}.json"
 python - "$tag" <<'PY'
 import json, sys
