@@ -39,6 +39,29 @@ INTER_SCALES = (1.0, 0.75, 0.15)     # config.py:71
 METRIC = "PointFlow iters/sec"
 
 
+def load_pretrained_hot_path_weights():
+    """The reference's shipped hot-path weights (outputs/dtu_wde3/model_pretrained.pth, keys flow_edge_conv.* /
+    flow_mlp.*), committed as the fixture tests/golden/flow_weights.npz."""
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "flow_weights.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def survey_8d_bytes_per_pass(H, W, V, B=1):
+    """SURVEY.md 8(d) algorithmic bytes of one 3-iteration pass, per stage (fp32, int64 indices as the public API
+    mandates, single-pass BatchNorm ideal): the numerators of `roofline_stage`."""
+    fetch = knn = chain = 0
+    prev = (H // 8) * (W // 8)
+    for s in IMG_SCALES:
+        h, w = int(H * s), int(W * s)
+        P = h * w * B
+        fetch += 28 * V * H * W * B + 4 * prev * B + 2720 * P + 60 * P
+        knn += 5 * P * 140
+        chain += 5 * P * 3108
+        prev = h * w
+    return {"fetch": fetch, "knn": knn, "edgeconv_mlp": chain}
+
+
 def workload_name(cfg, H, W, V, D):
     return "%s: DTU-shape %dx%d, %d src views (V=%d), %d depth hyp, %d flow iters, B=1 per pass" % (
         cfg, W, H, V - 1, V, D, len(IMG_SCALES))
@@ -137,16 +160,19 @@ def sample_clocks_stop(p, f):
 # --------------------------------------------------------------------------------------
 # CPU legs (the oracle is executed here ONLY as the reported baseline / reference arm)
 # --------------------------------------------------------------------------------------
-def cpu_reference_pass(cfg_name, steps, warmup, budget_s=240.0):
+def cpu_reference_pass(cfg_name, steps, warmup, budget_s=200.0):
     """Times the reference algorithm (oracle/pointflow_oracle.py, a restatement of the
     reference's Python; /root/reference itself does not exist on the GPU box) on the host
-    cores with all threads.  Returns (iters_per_s, ms_per_step, info)."""
+    cores.  A step is ALWAYS one whole 3-iteration pass of the same workload (same inputs, same
+    pretrained weights); when `steps + warmup` passes do not fit the time budget, FEWER passes are
+    timed (never a part of a pass) and the count actually timed is returned.
+    Returns (iters_per_s, ms_per_step, info)."""
     from oracle import pointflow_oracle as O
-    from pointmvsnet_b200.synthetic import make_pointflow_inputs, make_flow_params
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
     H, W, V, D = CONFIGS[cfg_name]
     cores = os.cpu_count() or 1
     inp = make_pointflow_inputs(H, W, V, 1, D, seed=0)
-    params = make_flow_params(seed=1)
+    params = O.params_from_state_dict(load_pretrained_hot_path_weights())
     scales, inters = IMG_SCALES, INTER_SCALES
 
     def one(sc, it):
@@ -155,9 +181,9 @@ def cpu_reference_pass(cfg_name, steps, warmup, budget_s=240.0):
                               inp["mean"], inp["std"], inp["img_hw"], params, img_scales=sc, inter_scales=it)
 
     # Give the reference its best thread count: PyTorch's CPU kernels on these per-call tensors
-    # get slower with too many threads (with all 128 host threads the 2-iteration sample took
-    # 154 s on the B200 host in round 1, against ~3 s on 8 threads in the build container), so
+    # get slower with too many threads (all 128 host threads are ~10x slower than 16 on the B200 host), so
     # iteration 1 is timed at a few pool sizes and the fastest is kept; `cores` reports it.
+    t_begin = time.time()
     best = None
     for nt in sorted({t for t in (8, 16, 32, 64, cores) if t <= cores}):
         torch.set_num_threads(nt)
@@ -171,34 +197,23 @@ def cpu_reference_pass(cfg_name, steps, warmup, budget_s=240.0):
         if dt > 4 * best[1]:
             break
     torch.set_num_threads(best[0])
-    t_it1 = best[1]
-    # A pass is 1 + 4 + 16 = 21 sub-cloud calls of equal size (25 600 points at C2), so its cost is
-    # proportional to the sub-clouds processed.  A step is the largest prefix of the pass that keeps
-    # the whole run inside the time bound; the rate is then scaled to the full pass by the
-    # sub-cloud count, so `value` stays the metric of the other arm (iterations of the 3-iteration
-    # pass per second).
-    n_sub = [int(round(sc * 8)) ** 2 for sc in scales]          # sub-clouds per iteration: 1, 4, 16
-    total_sub = sum(n_sub)
-    keep = len(scales)
-    while keep > 1 and t_it1 * sum(n_sub[:keep]) * (steps + warmup) > budget_s:
-        keep -= 1
-    frac = sum(n_sub[:keep]) / float(total_sub)
-    if keep == len(scales):
-        sample = "one full pass (%d iterations) of the same workload per step" % len(scales)
-    else:
-        sample = ("first %d of %d iterations of the pass per step (%d of %d equal-sized sub-clouds); time scaled by "
-                  "%d/%d to the full pass" % (keep, len(scales), sum(n_sub[:keep]), total_sub, total_sub, sum(n_sub[:keep])))
-    run_scales, run_inters = scales[:keep], inters[:keep]
-    for _ in range(warmup):
-        one(run_scales, run_inters)
+    n_sub = sum(int(round(sc * 8)) ** 2 for sc in scales)  # 21 equal-sized sub-cloud calls per pass
+    est_pass = best[1] * n_sub
+    left = budget_s - (time.time() - t_begin)
+    n_warm = warmup if est_pass * (warmup + 1) < left else (1 if est_pass * 2 < left else 0)
+    n_timed = int(max(1, min(steps, (left - n_warm * est_pass) // max(est_pass, 1e-3))))
+    for _ in range(n_warm):
+        one(scales, inters)
     times = []
-    for _ in range(steps):
+    for _ in range(n_timed):
         t0 = time.time()
-        one(run_scales, run_inters)
+        one(scales, inters)
         times.append(time.time() - t0)
-    ms = 1e3 * sum(times) / len(times) / frac   # per full pass
+    ms = 1e3 * sum(times) / len(times)
     value = len(scales) / (ms / 1e3)
-    return value, ms, {"cores": best[0], "host_cores": cores, "sample": sample, "kind": "port"}
+    sample = "%d whole pass(es) of the same workload timed (%d requested), %d warm-up pass(es)" % (n_timed, steps, n_warm)
+    return value, ms, {"cores": best[0], "host_cores": cores, "sample": sample, "kind": "port",
+                       "steps_timed": n_timed, "warmup_done": n_warm}
 
 
 def run_reference_arm(args):
@@ -209,9 +224,13 @@ def run_reference_arm(args):
     value, ms, info = cpu_reference_pass(args.config, max(1, args.steps), args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        # steps / warmup are the counts actually RUN (whole passes; fewer than requested when they would not fit
+        # the few-minute bound), so that steps * ms_per_step is the measured time
+        "steps": info["steps_timed"], "warmup": info["warmup_done"], "steps_requested": args.steps,
+        "warmup_requested": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, H, W, V, D)},
+        "config": {"workload": workload_name(args.config, H, W, V, D), "step": "one whole 3-iteration pass",
+                   "weights": "pretrained hot-path weights (tests/golden/flow_weights.npz)"},
         "cpu_baseline": {"value": value, "unit": "iters/s", "cores": info["cores"], "kind": info["kind"],
                          "host_cores": info["host_cores"], "sample": info["sample"]},
         "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -280,7 +299,7 @@ def run_ours(args):
     gpu_ins = [to_dev(h) for h in hosts]
     gpu_in = gpu_ins[0]
     pf = PointFlow().to(dev)
-    pf.load_state_dict(state_dict_from_params(make_flow_params(seed=1), pf.state_dict()))
+    pf.load_reference_state_dict(load_pretrained_hot_path_weights())
     pf.train()  # BN batch statistics, test.py:58
 
     def capture_set():
@@ -406,6 +425,7 @@ def run_ours(args):
 
     # ---- per-kernel CUDA-event timing (eager, not captured) for the roofline ---------------
     roofline = None
+    roofline_stage = None
     roofline_gemm = None
     kernel_table = None
     by_size = None
@@ -478,12 +498,37 @@ def run_ours(args):
                              "frac": round(ach / tf32_peak, 4), "ms_per_pass": round(gemm_ms, 4),
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)",
                              "note": "the contractions are memory bound (25 FLOP/B): see kernels[*].alg_GBps"}
+        # SURVEY.md 8(d) stage rooflines: the stage's single-pass algorithmic bytes over the summed event time of
+        # the kernels that implement it (the pyramid `transpose` launches and the BN running-statistics update are
+        # layout / bookkeeping outside 8(d)'s three stages and only enter the whole-pass line)
+        surv = survey_8d_bytes_per_pass(H, W, V)
+        stage_of = lambda n: ("fetch" if n in ("warp_source", "fused_fetch", "cam_setup") else
+                              "knn" if n == "knn3d" else
+                              "edgeconv_mlp" if (n.startswith("gemm_") or n.startswith("edge_") or n == "flow_head") else None)
+        st_ms = {}
+        for name, (ms, cnt) in agg.items():
+            k = stage_of(name)
+            if k is not None:
+                st_ms[k] = st_ms.get(k, 0.0) + ms / reps
+        roofline_stage = []
+        for k, nb in list(surv.items()) + [("whole_pass", sum(surv.values()))]:
+            ms = st_ms.get(k, 0.0) if k != "whole_pass" else tot / reps
+            if ms > 0:
+                gb = nb / (ms * 1e-3) / 1e9
+                roofline_stage.append({"stage": k, "bound": "hbm", "alg_bytes_per_pass": int(nb), "ms_per_pass": round(ms, 4),
+                                       "achieved": round(gb, 1), "peak": hbm_peak, "unit": "GB/s",
+                                       "frac": round(gb / hbm_peak, 4), "numerator": "SURVEY.md 8(d)"})
         dom = max(agg.items(), key=lambda kv: kv[1][0])[0]
         dom_ms_per_launch = agg[dom][0] / agg[dom][1]
         dom_bytes_per_launch = alg.get(dom, (0, 1))[0] / max(1, alg.get(dom, (0, 1))[1])
         achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(achieved / hbm_peak, 4), "traffic": traffic.get(dom), "peak_source": peak_src,
+                    "frac": round(achieved / hbm_peak, 4), "traffic": traffic.get(dom),
+                    "traffic_source": ("static: ncu --set full capture, profiles/dram_traffic.json (%s)" %
+                                       traffic.get("_capture", "see its _comment")) if traffic.get(dom) else None,
+                    "numerator": "bytes this kernel must read + write once given its boundaries (DESIGN.md 3); the "
+                                 "SURVEY 8(d) stage figures are in roofline_stage",
+                    "peak_source": peak_src,
                     "avg_launch_ms": round(dom_ms_per_launch, 5),
                     "alg_bytes_per_launch": int(dom_bytes_per_launch),
                     "kernel_sum_ms_per_pass": round(tot / reps, 4)}
@@ -507,7 +552,8 @@ def run_ours(args):
                        "views_in_flight": G,
                        "l2": "flushed between steps (256 MiB memset, untimed); per-step CUDA events, max over ranks",
                        "parallelism": "dp%d over reference views" % world, "bn": "batch statistics (train mode)",
-                       "weights": "random init, reference shapes"},
+                       "weights": "pretrained hot-path weights of the reference (tests/golden/flow_weights.npz)",
+                       "options": {k: _lib.get_option(k) for k in ("edge", "knn", "fetch", "gemm")}},
             "e2e": {"value": round(e2e_value, 2), "unit": "iters/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 5),
                     "how": "pinned host -> device copy of every step's inputs on a copy stream, double-buffered "
@@ -516,7 +562,8 @@ def run_ours(args):
                            "inside every timed step"},
             "gpu_launches": int(launches_per_pass * G * args.steps),
             "launches_per_step": int(launches_per_pass * G),
-            "clocks": clocks, "roofline": roofline, "roofline_gemm": roofline_gemm, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "roofline": roofline, "roofline_stage": roofline_stage, "roofline_gemm": roofline_gemm,
+            "cpu_baseline": cpu_baseline,
             "kernels": kernel_table,
             "per_iteration_size": by_size,
         }

@@ -54,12 +54,17 @@ int pmvs_set_gemm_mode(int mode);
 int pmvs_get_gemm_mode(void);
 
 /* Implementation switches of the fused path (process-wide, like the GEMM mode; for A/B measurements
- * and bisecting - every setting computes the same results):
- *   PMVS_OPT_EDGE   EdgeConv statistics/apply: 0 = 16 L2 gathers per point (round-1 kernels),
- *                   1 = TMA halo tile 8x4 pixels x 5 layers in shared memory, 2 = 16x4 tile
- *   PMVS_OPT_KNN    0 = sorted insertion, 1 = batched sorting network + bitonic merge (k=5,knn=16)
- *   PMVS_OPT_FETCH  0 = 4 taps per (hypothesis, view), 1 = hypotheses share the texel quad
- *   PMVS_OPT_GEMM   0 = points-as-M, shared-memory operands, 1 = weights in TMEM / points as N
+ * and bisecting - every setting computes the same results; the first value listed is the default):
+ *   PMVS_OPT_EDGE   EdgeConv statistics/apply: 1 = TMA halo tile (8x4 pixels x 5 layers) in shared memory,
+ *                   0 = 16 L2 gathers per point (the kernels the stand-alone EdgeConv operator uses)
+ *   PMVS_OPT_KNN    1 = batched sorting network + bitonic merge (kernel_size 5, knn 16),
+ *                   0 = sorted insertion (the kernel every other (kernel_size, knn) uses)
+ *   PMVS_OPT_FETCH  1 = consecutive hypotheses share the texel quad, packed fp32 math (3 CTAs / SM),
+ *                   2 = the same with 2 CTAs / SM and no register spills, 0 = 4 taps per (hypothesis, view)
+ *                   (the kernel used for V > 6)
+ *   PMVS_OPT_GEMM   2 = weights in tensor memory, points as N, persistent, cp.async staging 5 chunks deep,
+ *                   3 = 6 chunks deep, 1 = the same kernel with register prefetch (4 chunks),
+ *                   0 = points-as-M with shared-memory operands (the kernel plain-TF32 mode uses)
  *   PMVS_OPT_DEBUG_IDX  1 = also materialise int32 neighbour indices in the workspace */
 #define PMVS_OPT_EDGE 1
 #define PMVS_OPT_KNN 2
@@ -190,6 +195,12 @@ typedef struct pmvs_flow_shape {
                          (model.py:162-163) */
   float interval_scale; /* the hypothesis spacing is interval[b] * interval_scale (fp32 product,
                            model.py:301 inter_scale * depth_interval); use 1 if pre-multiplied */
+  /* Sub-cloud sharding over GPUs: the ratio^2 strided sub-clouds of an iteration are independent
+   * calls in the reference (model.py:236-267).  sub_count > 0 restricts this call to the sub-clouds
+   * [sub_begin, sub_begin + sub_count) in the reference's (i, j) loop order s = i*ratio + j: only their
+   * pixels of depth_out / prob_out are written, and the workspace is sized for sub_count sub-clouds.
+   * sub_count == 0 (default): all of them. */
+  int sub_begin, sub_count;
 } pmvs_flow_shape;
 
 /* bytes of device workspace pmvs_point_flow_iter needs for this shape */

@@ -24,6 +24,14 @@ void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memo
 
 // run-time implementation switches (common.cuh OPT_*); process-wide like the GEMM mode
 static std::atomic<int> g_opt[OPT_COUNT];
+static struct OptDefaults {
+  OptDefaults() {
+    g_opt[OPT_EDGE].store(1);   // TMA halo-tile EdgeConv
+    g_opt[OPT_KNN].store(1);    // batched sorting-network kNN
+    g_opt[OPT_FETCH].store(1);  // texel-quad sharing fetch
+    g_opt[OPT_GEMM].store(2);   // TMEM-stationary GEMM, cp.async staging ring
+  }
+} g_opt_defaults;
 int opt(int key) { return (key >= 0 && key < OPT_COUNT) ? g_opt[key].load(std::memory_order_relaxed) : 0; }
 
 // ---- optional per-launch event timing ------------------------------------------------------
@@ -127,7 +135,8 @@ __global__ void __launch_bounds__(256)
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct FlowPlan {
-  int S, hs, ws, N;
+  int S, hs, ws, N;  // S = sub-clouds PROCESSED by this call (all ratio^2 unless sharded)
+  int sub_begin;
   size_t R;  // rows = S * B * N
   size_t cam, feature, xyz, idx, le, ecat, h0, h1, h2, stats, total;
   size_t warp_src;     // the pyramid levels resized to the flow grid, [B,V,h,w,112]
@@ -151,7 +160,13 @@ static int make_plan(const pmvs_flow_shape* s, FlowPlan& p) {
   PMVS_REQUIRE(s->prev_h > 0 && s->prev_w > 0, "point_flow: bad previous depth size");
   for (int l = 0; l < 3; ++l) PMVS_REQUIRE(s->pyr_h[l] > 0 && s->pyr_w[l] > 0, "point_flow: bad pyramid size");
   PMVS_REQUIRE(s->flow_h > 1 && s->flow_w > 1, "point_flow: flow size must be > 1");
-  p.S = s->ratio * s->ratio;
+  const int s_all = s->ratio * s->ratio;
+  PMVS_REQUIRE(s->sub_count >= 0 && s->sub_begin >= 0 && s->sub_begin + s->sub_count <= s_all &&
+                   (s->sub_count > 0 || s->sub_begin == 0),
+               "point_flow: sub-cloud range [%d, %d) outside the %d sub-clouds", s->sub_begin,
+               s->sub_begin + s->sub_count, s_all);
+  p.S = s->sub_count > 0 ? s->sub_count : s_all;
+  p.sub_begin = s->sub_begin;
   p.hs = s->flow_h / s->ratio;
   p.ws = s->flow_w / s->ratio;
   p.N = PMVS_NUM_HYP * p.hs * p.ws;
@@ -376,7 +391,7 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
   f.src = warp_src;
   f.depth_prev = depth_prev; f.cam_blocks = cam; f.feature = feature; f.xyz = xyz;
   f.B = B; f.V = shape->V; f.h = shape->flow_h; f.w = shape->flow_w; f.hp = shape->prev_h; f.wp = shape->prev_w;
-  f.ratio = shape->ratio;
+  f.ratio = shape->ratio; f.sub_begin = p.sub_begin; f.sub_count = S;
   PMVS_TRY(launch_fused_fetch(f, st));
 
   // a10: neighbour lists.  The tile EdgeConv path consumes 1-byte candidate ids; the int32 row indices are only
@@ -439,7 +454,7 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
   HeadArgs h{};
   h.h2 = h2; h.stats = stats + p.st_mlp[2]; h.gamma = wts->mlp_gamma[2]; h.beta = wts->mlp_beta[2];
   h.w3 = wts->mlp_w[3]; h.depth_prev = depth_prev; h.interval = interval; h.depth_out = depth_out;
-  h.prob_out = prob_out; h.eps = wts->eps; h.interval_scale = shape->interval_scale; h.B = B; h.S = S; h.ratio = shape->ratio; h.h = shape->flow_h;
+  h.prob_out = prob_out; h.eps = wts->eps; h.interval_scale = shape->interval_scale; h.B = B; h.S = S; h.ratio = shape->ratio; h.sub_begin = p.sub_begin; h.h = shape->flow_h;
   h.w = shape->flow_w; h.hp = shape->prev_h; h.wp = shape->prev_w;
   PMVS_TRY(launch_flow_head(h, st));
 

@@ -197,6 +197,7 @@ struct FusedFetchParams {
   float* feature;           // [S,B,N,136]
   float* xyz;               // [S,B,3,N]
   int B, V, h, w, hp, wp, ratio;
+  int sub_begin, sub_count; // sub-clouds [sub_begin, sub_begin + sub_count) of the ratio^2 are produced
   int ppw, hs, ws, rlog2;   // set by the launcher: pixels per warp, sub-grid size, log2(ratio) or -1
 };
 // model.py:184 for the three levels at once: channels-last pyramids [B*V,hl,wl,16<<l] -> [B*V,h,w,112]
@@ -220,6 +221,7 @@ struct HeadArgs {
   float* prob_out;          // [B,5,h,w] or NULL
   float eps, interval_scale;
   int B, S, ratio, h, w, hp, wp;
+  int sub_begin;            // group s of this launch is sub-cloud sub_begin + s of the iteration
 };
 int launch_flow_head(const HeadArgs& a, cudaStream_t st);
 

@@ -402,7 +402,8 @@ __global__ void __launch_bounds__(256) flow_head_kernel(const HeadArgs a) {
   if (t >= a.B * P) return;
   const int b = t / P, pp = t - b * P;
   const int yy = pp / ws, xx = pp - yy * ws;
-  const int ii = s / a.ratio, jj = s - ii * a.ratio;
+  const int sg = s + a.sub_begin;  // sub-cloud index inside the iteration (model.py:244-245: i, j)
+  const int ii = sg / a.ratio, jj = sg - ii * a.ratio;
   const int Y = yy * a.ratio + ii, X = xx * a.ratio + jj;
   const size_t cloud_row = ((size_t)s * a.B + b) * N;
   float raw[PMVS_NUM_HYP];

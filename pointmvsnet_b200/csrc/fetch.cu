@@ -219,22 +219,27 @@ struct WarpSourceParams {
   float* out;           // [B][V*h*w + 1][112]: the last texel of every batch element is all zeros - the target of
                         // out-of-image taps (grid_sample's zeros padding, also for non-finite features)
   int h, w, V;
+  float rV;             // 1 / V
 };
 
 __global__ void __launch_bounds__(256) warp_source_kernel(const WarpSourceParams p) {
-  // grid: x = chunks of 256 float4s along one output row (w * 28 float4s), y = output row, z = b*V + v
+  // grid: x = chunks of 256 float4s along one output row (w * 28 float4s, memory order: a warp writes 512 contiguous
+  // bytes), y = output row, z = b*V + v.  (A variant with level-uniform blocks - no per-thread level selects - measured
+  // 40 % slower: its stores are 64..256-byte pieces at a 448-byte pitch.)
   const int xi = blockIdx.x * 256 + threadIdx.x;
   if (xi >= p.w * FETCH_C4) return;
   const int x = xi / FETCH_C4, c4 = xi - x * FETCH_C4;
   const int y = blockIdx.y;
-  const long long bv = blockIdx.z;
-  const long long bb = bv / p.V;
-  float* outp = p.out + ((bv * p.h + y) * (long long)p.w * FETCH_C4 + bb * FETCH_C4 + xi) * 4;
+  const int bv = blockIdx.z;
+  const int bb = (int)(((float)bv + 0.5f) * p.rV);  // bv / V (exact for bv < 2^22)
+  // 32-bit offsets inside one view's maps (checked by the launcher); one 64-bit base per view
+  const size_t out_view = ((size_t)bv * p.h * p.w + bb) * FETCH_CH;  // + bb: one zero texel per earlier batch element
+  float* outp = p.out + out_view + ((unsigned)(y * p.w) * FETCH_C4 + xi) * 4u;
   if (xi < FETCH_C4 && y == 0 && bv - bb * p.V == p.V - 1)  // the batch element's trailing zero texel
-    st4(p.out + ((bb + 1) * ((long long)p.V * p.h * p.w + 1) - 1) * FETCH_CH + xi * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    st4(p.out + ((size_t)(bb + 1) * ((size_t)p.V * p.h * p.w + 1) - 1) * FETCH_CH + xi * 4, make_float4(0.f, 0.f, 0.f, 0.f));
   const int l = c4 < 4 ? 0 : (c4 < 12 ? 1 : 2);
   const int cq = c4 - (l == 0 ? 0 : (l == 1 ? 4 : 12));
-  const int C4 = 4 << l;
+  const int lg = 4 + l;  // log2(channels of the level)
   const int hi = l == 0 ? p.hl[0] : (l == 1 ? p.hl[1] : p.hl[2]);  // (no dynamic indexing of the parameter struct)
   const int wi = l == 0 ? p.wl[0] : (l == 1 ? p.wl[1] : p.wl[2]);
   const float* lvl = l == 0 ? p.pyr[0] : (l == 1 ? p.pyr[1] : p.pyr[2]);
@@ -249,19 +254,20 @@ __global__ void __launch_bounds__(256) warp_source_kernel(const WarpSourceParams
   const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
   const float ly1 = __fsub_rn(fy, (float)y0), ly0 = __fsub_rn(1.f, ly1);
   const float lx1 = __fsub_rn(fx, (float)x0), lx0 = __fsub_rn(1.f, lx1);
-  const float* base = lvl + (bv * hi * wi * C4 + cq) * 4;
-  const int r0 = y0 * wi, r1 = y1 * wi;  // < 2^31 texels per level map (checked by the launcher)
-  const float4 v00 = ldg4(base + (size_t)(r0 + x0) * (C4 * 4)), v01 = ldg4(base + (size_t)(r0 + x1) * (C4 * 4));
-  const float4 v10 = ldg4(base + (size_t)(r1 + x0) * (C4 * 4)), v11 = ldg4(base + (size_t)(r1 + x1) * (C4 * 4));
-  float4 o;  // h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11), ATen's association
-  o.x = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.x), __fmul_rn(lx1, v01.x))),
-                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.x), __fmul_rn(lx1, v11.x))));
-  o.y = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.y), __fmul_rn(lx1, v01.y))),
-                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.y), __fmul_rn(lx1, v11.y))));
-  o.z = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.z), __fmul_rn(lx1, v01.z))),
-                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.z), __fmul_rn(lx1, v11.z))));
-  o.w = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00.w), __fmul_rn(lx1, v01.w))),
-                  __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10.w), __fmul_rn(lx1, v11.w))));
+  const float* base = lvl + (((size_t)bv * hi * wi) << lg) + cq * 4;
+  const unsigned r0 = (unsigned)(y0 * wi) << lg, r1 = (unsigned)(y1 * wi) << lg;
+  const unsigned q0 = (unsigned)x0 << lg, q1 = (unsigned)x1 << lg;
+  const float4 v00 = ldg4(base + r0 + q0), v01 = ldg4(base + r0 + q1);
+  const float4 v10 = ldg4(base + r1 + q0), v11 = ldg4(base + r1 + q1);
+  // h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11), ATen's association, on fp32 pairs
+  const f32x2 LX0 = pack2(lx0, lx0), LX1 = pack2(lx1, lx1), LY0 = pack2(ly0, ly0), LY1 = pack2(ly1, ly1);
+  const f32x2 a_lo = mul2(LY0, add2(mul2(LX0, pack2(v00.x, v00.y)), mul2(LX1, pack2(v01.x, v01.y))));
+  const f32x2 b_lo = mul2(LY1, add2(mul2(LX0, pack2(v10.x, v10.y)), mul2(LX1, pack2(v11.x, v11.y))));
+  const f32x2 a_hi = mul2(LY0, add2(mul2(LX0, pack2(v00.z, v00.w)), mul2(LX1, pack2(v01.z, v01.w))));
+  const f32x2 b_hi = mul2(LY1, add2(mul2(LX0, pack2(v10.z, v10.w)), mul2(LX1, pack2(v11.z, v11.w))));
+  float4 o;
+  unpack2(add2(a_lo, b_lo), o.x, o.y);
+  unpack2(add2(a_hi, b_hi), o.z, o.w);
   st4(outp, o);
 }
 
@@ -365,6 +371,13 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32, MINB) fused_fetch_kernel(con
   for (int k = 0; k < p.ppw; ++k) {
     const int X = X0 + k * 4;
     if (X >= w) break;  // warp-uniform
+    {
+      // sub-cloud sharding (model.py:236-267 units spread over GPUs): only pixels of the sub-clouds
+      // [sub_begin, sub_begin + sub_count) are produced; rows are numbered from sub_begin
+      const int xq = p.rlog2 >= 0 ? X >> p.rlog2 : X / p.ratio;
+      const int sc = ii * p.ratio + (X - xq * p.ratio) - p.sub_begin;
+      if (sc < 0 || sc >= p.sub_count) continue;  // warp-uniform
+    }
 
     int xs = (int)floorf((float)X * nsx);
     xs = xs < p.wp - 1 ? xs : p.wp - 1;
@@ -436,7 +449,7 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32, MINB) fused_fetch_kernel(con
     // ---- phase 2: fetch + variance over views ---------------------------------------------------
     const int xx = p.rlog2 >= 0 ? X >> p.rlog2 : X / p.ratio;
     const int jj = X - xx * p.ratio;
-    const int cloud = (ii * p.ratio + jj) * p.B + b;
+    const int cloud = (ii * p.ratio + jj - p.sub_begin) * p.B + b;
     float* frow0 = p.feature + ((size_t)cloud * Npts + (size_t)yy * wsub + xx) * PMVS_FEAT_CH;  // hypothesis 0
     if (SHARE) {
       // Views outermost.  Consecutive hypotheses of a pixel project ~0.1 texel apart along the epipolar line, so a
@@ -454,7 +467,7 @@ __global__ void __launch_bounds__(FETCH_WARPS * 32, MINB) fused_fetch_kernel(con
 #pragma unroll
           for (int m = 0; m < PMVS_NUM_HYP; ++m) {
             const Desc* dm = desc + m * V + v;
-            if (m == 0 || !((eqmask >> (m * V + v)) & 1u)) {  // warp-uniform
+            if (m == 0 || !((eqmask >> (m * V + v)) & 1u)) {  // warp-uniform: another texel quad than hypothesis m - 1
               const uint4 o = *reinterpret_cast<const uint4*>(dm->o);
               t0 = __ldg(src + o.x); t1 = __ldg(src + o.y); t2 = __ldg(src + o.z); t3 = __ldg(src + o.w);
             }
@@ -619,11 +632,12 @@ int launch_warp_source(const float* const pyr[3], const int hl[3], const int wl[
                        int w, cudaStream_t st) {
   WarpSourceParams q{};
   for (int l = 0; l < 3; ++l) { q.pyr[l] = pyr[l]; q.hl[l] = hl[l]; q.wl[l] = wl[l]; }
-  q.out = out; q.h = h; q.w = w; q.V = V;
+  q.out = out; q.h = h; q.w = w; q.V = V; q.rV = 1.0f / (float)V;
   const int BV = B * V;
   PMVS_REQUIRE(B > 0 && V > 0 && BV <= 65535 && h > 0 && h <= 65535 && w > 0, "warp_source: bad shape");
+  PMVS_REQUIRE((long long)h * w * FETCH_CH < (1ll << 31), "warp_source: flow grid %dx%d too large", h, w);
   for (int l = 0; l < 3; ++l) {
-    PMVS_REQUIRE((long long)hl[l] * wl[l] < (1ll << 31), "warp_source: level %d too large", l);
+    PMVS_REQUIRE((long long)hl[l] * wl[l] * (16 << l) < (1ll << 31), "warp_source: level %d too large", l);
     q.sy[l] = (float)hl[l] / (float)h; q.sx[l] = (float)wl[l] / (float)w;
   }
   dim3 grid(cdiv((long long)w * FETCH_C4, 256), h, BV);

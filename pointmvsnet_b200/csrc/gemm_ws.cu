@@ -15,7 +15,7 @@
 //     instead of 112) and issues 2 MMAs (M=128, N=128, K=8):  [W_hi;W_lo] * X_hi  and  [W_hi;W_lo] * X_lo.
 //     Accumulator lanes [0,64) hold W_hi*X, lanes [64,128) hold W_lo*X; the epilogue adds them.
 //     cout = 128 uses two A operands (W_hi, W_lo) and two accumulators (3 MMAs per k-step).
-//   * warp-specialised, persistent: 8 producer warps (coalesced 128-bit global loads two chunks ahead
+//   * warp-specialised, persistent: 16 producer warps (coalesced 128-bit global loads four chunks ahead
 //     in registers -> fused input BatchNorm+ReLU -> TF32 hi/lo split -> K-major SWIZZLE_128B stores
 //     into a 4-stage mbarrier ring), 1 MMA warp (one elected thread: tcgen05.mma, tcgen05.commit frees
 //     the stage), 4 epilogue warps (tcgen05.ld of one accumulator while the MMAs fill the other).
@@ -35,25 +35,33 @@ namespace ws {
 
 constexpr int NT = 128;                       // points per tile == UMMA N
 constexpr int KC = 32;                        // fp32 K columns per chunk == one 128-byte swizzle row
-constexpr int STAGES = 4;
 constexpr int PLANE_BYTES = NT * KC * 4;      // 16 KB
 constexpr int STAGE_BYTES = 2 * PLANE_BYTES;  // X_hi, X_lo
-constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
 constexpr int MMA_WARP = EPI_WARPS;           // warp 4
 constexpr int PROD_WARP0 = EPI_WARPS + 1;     // warps 5..12
 constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int THREADS = 32 * (EPI_WARPS + 1 + PROD_WARPS);  // 416
+constexpr int THREADS = 32 * (EPI_WARPS + 1 + PROD_WARPS);  // 672
 constexpr int XPITCH = 36;                    // floats per accumulator-lane row of the epilogue staging buffer
 constexpr int XBUF_BYTES = 128 * XPITCH * 4;  // 18 432 B: 128 lanes x 32 points (+ pad) of one accumulator slab
-constexpr int PF = 4;                         // chunks of global loads in flight per producer thread
 constexpr int MAXK = 224;
-constexpr int A_LD = NT * 8 / PROD_THREADS;   // float4 loads per producer thread and chunk (4)
+constexpr int A_LD = NT * 8 / PROD_THREADS;   // float4 loads per producer thread and chunk (2)
 
-constexpr int SM_RING = 0;
-constexpr int SM_XBUF = SM_RING + STAGES * STAGE_BYTES;
-constexpr int SM_BN = SM_XBUF + 2 * XBUF_BYTES;
-constexpr int SM_BAR = SM_BN + 4 * MAXK * 4;
-constexpr int SM_TOTAL = SM_BAR + 128 + 1024 /* alignment slack */;
+// Shared-memory layout.  ASYNC = 0: the producers prefetch through registers (4 chunks ahead) into a 4-stage operand
+// ring.  ASYNC = N > 0: the raw fp32 chunks travel global -> shared memory with cp.async (LDGSTS, no registers
+// held) into an N-stage staging ring, N - 1 chunks ahead; the producer converts its own pieces from there into a
+// 2-stage operand ring.  16 KB per staging stage, 32 KB per operand stage (X_hi | X_lo).
+template <int ASYNC>
+struct Layout {
+  static constexpr int NST = ASYNC > 0 ? 2 : 4;  // operand stages
+  static constexpr int RING = 0;
+  static constexpr int STAGING = RING + NST * STAGE_BYTES;
+  static constexpr int XBUF = STAGING + ASYNC * PLANE_BYTES;
+  static constexpr int BN = XBUF + 2 * XBUF_BYTES;
+  static constexpr int BAR = BN + 4 * MAXK * 4;
+  static constexpr int TOTAL = BAR + 128;
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+};
 
 constexpr int TM_A = 0;      // A operand(s): columns [0, 256)
 constexpr int TM_A2 = 128;   // second A operand (W_lo) when cout = 128
@@ -126,6 +134,15 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                : "memory");
 }
+// explicit shared-space accesses on 32-bit shared addresses (STS.128 / LDS.128, never generic ST.E / LD.E)
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 struct TileRange {
@@ -138,12 +155,16 @@ __device__ __forceinline__ TileRange my_tiles(int total) {
   return TileRange{lo, hi - lo};
 }
 
-template <int COUT>
+template <int COUT, bool IN_BN, int ASYNC>
 __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
+  using LY = Layout<ASYNC>;
+  constexpr int STAGES = LY::NST;
+  constexpr int SM_RING = LY::RING, SM_STAGING = LY::STAGING, SM_XBUF = LY::XBUF, SM_BN = LY::BN, SM_BAR = LY::BAR;
+  constexpr int PF = ASYNC > 0 ? ASYNC - 1 : 4;  // chunks of global loads in flight per producer thread
   constexpr bool STACKED = COUT <= 64;
   constexpr int ACC_BUFS = STACKED ? 2 : 1;
-  extern __shared__ unsigned char ws_smem_raw[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)ws_smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B operands need 1024-byte alignment
+  const uint32_t smem_base = smem_u32(smem);
   float* sBN = (float*)(smem + SM_BN);  // mean, istd, gamma, beta x MAXK
   uint64_t* bars = (uint64_t*)(smem + SM_BAR);
   // bars: full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]; then the TMEM base slot
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tpg = (a.rows_per_group + NT - 1) / NT;  // tiles per group
   const TileRange tr = my_tiles(a.groups * tpg);
-  const bool in_bn = a.in_stats != nullptr;
+  constexpr bool in_bn = IN_BN;
 
   if (warp == MMA_WARP) {
     if (lane == 0) {
@@ -225,23 +246,66 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
   if (warp >= PROD_WARP0) {
     // =============================== producers ==========================================================
     const int ptid = tid - PROD_WARP0 * 32;
-    const int pc = ptid & 7;    // 16-byte piece inside the 128-byte row
-    const int prow = ptid >> 3;  // 0..31 ; rows prow + 32*i
+    const int pc = ptid & 7;     // 16-byte piece inside the 128-byte row
+    const int prow = ptid >> 3;  // first row of this thread; rows prow + ROWS_STEP * i
+    constexpr int ROWS_STEP = PROD_THREADS / 8;
     const int total = tr.count * nch;
     int cur_g = -1;
-    float4 buf[PF + 1][A_LD];
+    float4 buf[ASYNC > 0 ? 1 : PF + 1][A_LD];
+    // byte offsets of this thread's pieces inside a K-major SWIZZLE_128B plane (the same for every chunk)
+    int soff[A_LD];
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      const int r = prow + ROWS_STEP * i;
+      soff[i] = (r >> 3) * 1024 + (r & 7) * 128 + ((pc ^ (r & 7)) << 4);
+    }
 
     // (tile, chunk) cursors of the load stream and of the store stream: both walk items 0, 1, 2, .. in order, so
-    // they advance incrementally (no integer divisions on the per-chunk path)
+    // they advance incrementally (no integer divisions / 64-bit multiplies on the per-chunk path)
     struct Cursor {
       int g, row0, c;
+      const float* ptr;  // load stream only: this thread's first piece of the current chunk
     };
     Cursor ci, cp;
     {
       const int t0 = tr.first;
       ci.g = t0 / tpg; ci.row0 = (t0 - ci.g * tpg) * NT; ci.c = 0;
+      ci.ptr = a.x + ((size_t)ci.g * a.rows_per_group + ci.row0 + prow) * a.ldx + pc * 4;
       cp = ci;
     }
+    const bool last_kvalid = (nch - 1) * KC + pc * 4 < K;  // K % 32 != 0: the last chunk is partly padding
+    const size_t tile_step = (size_t)NT * a.ldx - (size_t)(nch - 1) * KC;
+    int n_issued = 0;
+    auto issue = [&](float4 (&xa)[A_LD]) {
+      const int rows_valid = a.rows_per_group - ci.row0;  // >= NT except in the last tile of a group
+      const bool kvalid = ci.c != nch - 1 || last_kvalid;
+#pragma unroll
+      for (int i = 0; i < A_LD; ++i) {
+        const int r = prow + ROWS_STEP * i;
+        const bool ok = kvalid && r < rows_valid;
+        if (ASYNC > 0) {
+          // 16 bytes global -> this thread's own slot of the staging stage; src-size 0 zero-fills (padding rows / columns)
+          const uint32_t dst = smem_base + SM_STAGING + (n_issued % ASYNC) * PLANE_BYTES + (ptid + PROD_THREADS * i) * 16;
+          const float* src = ok ? ci.ptr + (size_t)(ROWS_STEP * i) * a.ldx : a.x;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        } else {
+          xa[i] = ok ? ldg4(ci.ptr + (size_t)(ROWS_STEP * i) * a.ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      ++n_issued;
+      if (++ci.c == nch) {
+        ci.c = 0;
+        ci.row0 += NT;
+        ci.ptr += tile_step;
+        if (ci.row0 >= a.rows_per_group) {  // next group: its rows follow the previous group's (ragged tail skipped)
+          ci.row0 = 0;
+          ++ci.g;
+          ci.ptr = a.x + ((size_t)ci.g * a.rows_per_group + prow) * a.ldx + pc * 4;
+        }
+      } else {
+        ci.ptr += KC;
+      }
+    };
     auto advance = [&](Cursor& cu) {
       if (++cu.c == nch) {
         cu.c = 0;
@@ -252,54 +316,51 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
         }
       }
     };
-    auto issue = [&](float4 (&xa)[A_LD]) {
-      const int rows_valid = min(NT, a.rows_per_group - ci.row0);
-      const float* xrow = a.x + ((size_t)ci.g * a.rows_per_group + ci.row0 + prow) * a.ldx + ci.c * KC + pc * 4;
-      const bool kvalid = ci.c * KC + pc * 4 < K;
-#pragma unroll
-      for (int i = 0; i < A_LD; ++i) {
-        const int r = prow + 32 * i;
-        xa[i] = (kvalid && r < rows_valid) ? ldg4(xrow + (size_t)(32 * i) * a.ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      advance(ci);
-    };
     auto put = [&](const float4 (&xa)[A_LD], int n) {
-      const int g = cp.g, c = cp.c;
-      const int rows_valid = min(NT, a.rows_per_group - cp.row0);
-      if (in_bn && g != cur_g) {  // uniform over all producer threads: they walk the same item sequence
-        named_bar_sync(1, PROD_THREADS);
-        const double* s = a.in_stats + (size_t)g * 2 * K;
-        for (int cc = ptid; cc < K; cc += PROD_THREADS) {
-          const BnCoef k = bn_coef(s[cc], s[K + cc], a.in_count, a.eps);
-          sBN[cc] = k.mean;
-          sBN[MAXK + cc] = k.invstd;
-          sBN[2 * MAXK + cc] = a.in_gamma[cc];
-          sBN[3 * MAXK + cc] = a.in_beta[cc];
+      const int k0 = cp.c * KC + pc * 4;
+      if (IN_BN) {
+        const int g = cp.g;
+        if (g != cur_g) {  // uniform over all producer threads: they walk the same item sequence
+          named_bar_sync(1, PROD_THREADS);
+          const double* s = a.in_stats + (size_t)g * 2 * K;
+          for (int cc = ptid; cc < K; cc += PROD_THREADS) {
+            const BnCoef k = bn_coef(s[cc], s[K + cc], a.in_count, a.eps);
+            sBN[cc] = k.mean;
+            sBN[MAXK + cc] = k.invstd;
+            sBN[2 * MAXK + cc] = a.in_gamma[cc];
+            sBN[3 * MAXK + cc] = a.in_beta[cc];
+          }
+          named_bar_sync(1, PROD_THREADS);
+          cur_g = g;
         }
-        named_bar_sync(1, PROD_THREADS);
-        cur_g = g;
       }
       const int stage = n % STAGES;
       mbar_wait(bar_empty(stage), (uint32_t)(((n / STAGES) & 1) ^ 1));
-      unsigned char* hi_plane = smem + SM_RING + stage * STAGE_BYTES;
-      const int k0 = c * KC + pc * 4;
-      const bool kvalid = k0 < K;
+      const uint32_t hi_plane = smem_base + SM_RING + stage * STAGE_BYTES;
+      if (ASYNC > 0) {
+        // every call is preceded by exactly one commit (possibly of an empty group), so "at most PF groups pending"
+        // means the group of chunk n has landed; the thread reads back only what it copied itself
+        asm volatile("cp.async.wait_group %0;" ::"n"(PF) : "memory");
+      }
 #pragma unroll
       for (int i = 0; i < A_LD; ++i) {
-        const int r = prow + 32 * i;
-        float4 v = xa[i];
-        if (in_bn && kvalid && r < rows_valid) {
-          v.x = fmaxf(bn_apply(v.x, sBN[k0 + 0], sBN[MAXK + k0 + 0], sBN[2 * MAXK + k0 + 0], sBN[3 * MAXK + k0 + 0]), 0.f);
-          v.y = fmaxf(bn_apply(v.y, sBN[k0 + 1], sBN[MAXK + k0 + 1], sBN[2 * MAXK + k0 + 1], sBN[3 * MAXK + k0 + 1]), 0.f);
-          v.z = fmaxf(bn_apply(v.z, sBN[k0 + 2], sBN[MAXK + k0 + 2], sBN[2 * MAXK + k0 + 2], sBN[3 * MAXK + k0 + 2]), 0.f);
-          v.w = fmaxf(bn_apply(v.w, sBN[k0 + 3], sBN[MAXK + k0 + 3], sBN[2 * MAXK + k0 + 3], sBN[3 * MAXK + k0 + 3]), 0.f);
+        float4 v = ASYNC > 0 ? lds128(smem_base + SM_STAGING + (n % (ASYNC > 0 ? ASYNC : 1)) * PLANE_BYTES + (ptid + PROD_THREADS * i) * 16)
+                             : xa[i];
+        if (IN_BN) {
+          // rows / columns beyond the valid range were loaded as zeros and must stay zero
+          const int r = prow + ROWS_STEP * i;
+          if (k0 < K && r < a.rows_per_group - cp.row0) {
+            v.x = fmaxf(bn_apply(v.x, sBN[k0 + 0], sBN[MAXK + k0 + 0], sBN[2 * MAXK + k0 + 0], sBN[3 * MAXK + k0 + 0]), 0.f);
+            v.y = fmaxf(bn_apply(v.y, sBN[k0 + 1], sBN[MAXK + k0 + 1], sBN[2 * MAXK + k0 + 1], sBN[3 * MAXK + k0 + 1]), 0.f);
+            v.z = fmaxf(bn_apply(v.z, sBN[k0 + 2], sBN[MAXK + k0 + 2], sBN[2 * MAXK + k0 + 2], sBN[3 * MAXK + k0 + 2]), 0.f);
+            v.w = fmaxf(bn_apply(v.w, sBN[k0 + 3], sBN[MAXK + k0 + 3], sBN[2 * MAXK + k0 + 3], sBN[3 * MAXK + k0 + 3]), 0.f);
+          }
         }
-        const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((pc ^ (r & 7)) << 4);
         float4 hi, lo;
         hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
         lo.x = __fsub_rn(v.x, hi.x); lo.y = __fsub_rn(v.y, hi.y); lo.z = __fsub_rn(v.z, hi.z); lo.w = __fsub_rn(v.w, hi.w);
-        *reinterpret_cast<float4*>(hi_plane + off) = hi;
-        *reinterpret_cast<float4*>(hi_plane + PLANE_BYTES + off) = lo;
+        sts128(hi_plane + soff[i], hi);
+        sts128(hi_plane + PLANE_BYTES + soff[i], lo);
       }
       // No fence.proxy.async here: it lowers to MEMBAR.ALL.CTA, which would wait for this thread's PF chunks of
       // global loads in flight and serialise the prefetch.  The stores are published by the release-arrive below;
@@ -309,18 +370,30 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
       advance(cp);
     };
 
-    // PF chunks (PF x 16 KB per SM) of loads in flight while one is converted and stored: at ~1.5 us of loaded
-    // DRAM latency the SM's share of the HBM bandwidth needs ~50 KB in flight
+    // PF chunks (PF x 16 KB per SM) of loads in flight while one is converted and stored: at ~2 us of loaded
+    // DRAM latency the SM's share of the HBM bandwidth needs ~100 KB in flight
+    if (ASYNC > 0) {
+      for (int i = 0; i < PF; ++i) {
+        if (i < total) issue(buf[0]);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      for (int m = 0; m < total; ++m) {
+        if (m + PF < total) issue(buf[0]);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        put(buf[0], m);
+      }
+    } else {
 #pragma unroll
-    for (int i = 0; i < PF; ++i)
-      if (i < total) issue(buf[i]);
-    for (int n = 0; n < total; n += PF + 1) {
+      for (int i = 0; i < PF; ++i)
+        if (i < total) issue(buf[i]);
+      for (int n = 0; n < total; n += PF + 1) {
 #pragma unroll
-      for (int u = 0; u <= PF; ++u) {
-        const int m = n + u;
-        if (m < total) {
-          if (m + PF < total) issue(buf[(u + PF) % (PF + 1)]);
-          put(buf[u], m);
+        for (int u = 0; u <= PF; ++u) {
+          const int m = n + u;
+          if (m < total) {
+            if (m + PF < total) issue(buf[ASYNC > 0 ? 0 : (u + PF) % (PF + 1)]);
+            put(buf[ASYNC > 0 ? 0 : u], m);
+          }
         }
       }
     }
@@ -342,7 +415,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
           fence_proxy_async();  // the producers' generic-proxy stores (acquired above) -> the tensor core's async proxy
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t x_hi = smem_u32(smem + SM_RING + stage * STAGE_BYTES), x_lo = x_hi + PLANE_BYTES;
+            const uint32_t x_hi = smem_base + SM_RING + stage * STAGE_BYTES, x_lo = x_hi + PLANE_BYTES;
             const int ksteps = min(KC, K - c * KC) / 8;
             for (int j = 0; j < ksteps; ++j) {
               const uint32_t acc = (c == 0 && j == 0) ? 0u : 1u;
@@ -367,7 +440,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
     // =============================== epilogue ===========================================================
     const int q = warp;  // TMEM lane quarter
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* const xs = (float*)(smem + SM_XBUF);  // 2 x [128 lanes][XPITCH]
+    const uint32_t xs = smem_base + SM_XBUF;  // 2 x [128 lanes][XPITCH] floats
     // stacked: accumulator lanes [0,64) = W_hi * X, [64,128) = W_lo * X of channels [0,64).  A slab (32 points) of
     // all 128 lanes goes through shared memory; afterwards warp q adds the halves of points [8q, 8q+8) for the
     // channels `lane` and `lane + 32` and stores them (32 consecutive channels of a point = one 128-byte line).
@@ -413,19 +486,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
         float v[32];
         tmem_ld32(d0 + slab * 32, v);
         if (STACKED) {
-          float* xb = xs + (slab & 1) * (XBUF_BYTES / 4);
-          float* xrow = xb + (q * 32 + lane) * XPITCH;
+          const uint32_t xb = xs + (slab & 1) * XBUF_BYTES;
+          const uint32_t xrow = xb + (q * 32 + lane) * (XPITCH * 4);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(xrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 32; j += 4) sts128(xrow + j * 4, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
           named_bar_sync(2 + (slab & 1), EPI_WARPS * 32);
           const int p0 = slab * 32 + q * 8;  // first of this warp's 8 points of the slab
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int ch = chs[h];
-            const float* hi = xb + ch * XPITCH + q * 8;
-            const float* lo = hi + 64 * XPITCH;
-            const float4 h0 = *reinterpret_cast<const float4*>(hi), h1 = *reinterpret_cast<const float4*>(hi + 4);
-            const float4 l0 = *reinterpret_cast<const float4*>(lo), l1 = *reinterpret_cast<const float4*>(lo + 4);
+            const uint32_t hi = xb + (ch * XPITCH + q * 8) * 4;
+            const uint32_t lo = hi + 64 * XPITCH * 4;
+            const float4 h0 = lds128(hi), h1 = lds128(hi + 16);
+            const float4 l0 = lds128(lo), l1 = lds128(lo + 16);
             const float o[8] = {h0.x + l0.x, h0.y + l0.y, h0.z + l0.z, h0.w + l0.w,
                                 h1.x + l1.x, h1.y + l1.y, h1.z + l1.z, h1.w + l1.w};
             if (ch < COUT) {
@@ -497,10 +570,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
   }
 }
 
-template <int COUT>
-static int launch_one(const GemmArgs& a, cudaStream_t st, const char* name) {
+template <int COUT, bool IN_BN, int ASYNC>
+static int launch_pf(const GemmArgs& a, cudaStream_t st, const char* name) {
+  constexpr int SM_TOTAL = Layout<ASYNC>::TOTAL;
   static unsigned long long smem_done = 0;
-  PMVS_TRY(ensure_dyn_smem(gemm_ws_kernel<COUT>, SM_TOTAL, smem_done, "gemm_ws"));
+  PMVS_TRY((ensure_dyn_smem(gemm_ws_kernel<COUT, IN_BN, ASYNC>, SM_TOTAL, smem_done, "gemm_ws")));
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -510,8 +584,16 @@ static int launch_one(const GemmArgs& a, cudaStream_t st, const char* name) {
   const long long tiles = (long long)a.groups * cdiv(a.rows_per_group, NT);
   const int grid = (int)std::min<long long>(tiles, num_sms);
   prof_begin(name, st);
-  gemm_ws_kernel<COUT><<<grid, THREADS, SM_TOTAL, st>>>(a);
+  gemm_ws_kernel<COUT, IN_BN, ASYNC><<<grid, THREADS, SM_TOTAL, st>>>(a);
   return check_launch("gemm_ws_kernel", st);
+}
+template <int COUT, bool IN_BN>
+static int launch_one(const GemmArgs& a, cudaStream_t st, const char* name) {
+  switch (opt(OPT_GEMM)) {
+    case 2: return launch_pf<COUT, IN_BN, 6>(a, st, name);  // cp.async staging ring, 5 chunks (80 KB) in flight
+    case 3: return launch_pf<COUT, IN_BN, 7>(a, st, name);  // 6 chunks (96 KB) in flight
+  }
+  return launch_pf<COUT, IN_BN, 0>(a, st, name);            // register prefetch, 4 chunks (64 KB) in flight
 }
 
 }  // namespace ws
@@ -521,11 +603,14 @@ int launch_gemm_ws(const GemmArgs& a, cudaStream_t st, const char* name) {
   if (a.cin % 8 != 0 || a.cin > ws::MAXK || a.ldx % 4 != 0 || a.groups <= 0 || a.rows_per_group <= 0) return -1;
   if (((uintptr_t)a.x & 15) || ((uintptr_t)a.w & 15)) return -1;
   if ((long long)a.groups * cdiv(a.rows_per_group, ws::NT) >= (1ll << 31) / ws::MAXK) return -1;
+  const bool bn = a.in_stats != nullptr;
   switch (a.cout) {
-    case 16: return ws::launch_one<16>(a, st, name);
-    case 32: return ws::launch_one<32>(a, st, name);
-    case 64: return ws::launch_one<64>(a, st, name);
-    case 128: return a.cin <= 128 ? ws::launch_one<128>(a, st, name) : -1;
+    case 16: return bn ? ws::launch_one<16, true>(a, st, name) : ws::launch_one<16, false>(a, st, name);
+    case 32: return bn ? ws::launch_one<32, true>(a, st, name) : ws::launch_one<32, false>(a, st, name);
+    case 64: return bn ? ws::launch_one<64, true>(a, st, name) : ws::launch_one<64, false>(a, st, name);
+    case 128:
+      if (a.cin > 128) return -1;
+      return bn ? ws::launch_one<128, true>(a, st, name) : ws::launch_one<128, false>(a, st, name);
   }
   return -1;
 }

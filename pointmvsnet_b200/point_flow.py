@@ -162,7 +162,7 @@ class PointFlow(nn.Module):
 
     # ------------------------------------------------------------------ shape / workspace
     @staticmethod
-    def make_shape(B, V, pyr_hw, prev_hw, img_hw, image_scale, is_test, interval_scale=1.0):
+    def make_shape(B, V, pyr_hw, prev_hw, img_hw, image_scale, is_test, interval_scale=1.0, sub_range=None):
         s = FlowShape()
         s.B, s.V = B, V
         for l in range(3):
@@ -173,6 +173,10 @@ class PointFlow(nn.Module):
         s.ratio = _ratio_for(image_scale, is_test)
         s.is_test = 1 if is_test else 0
         s.interval_scale = float(interval_scale)
+        if sub_range is not None:  # (first sub-cloud, count) in the reference's (i, j) loop order, model.py:244-245
+            s.sub_begin, s.sub_count = int(sub_range[0]), int(sub_range[1])
+            if s.sub_count <= 0 or s.sub_begin < 0 or s.sub_begin + s.sub_count > s.ratio * s.ratio:
+                raise RuntimeError("PointFlow: sub_range %r outside the %d sub-clouds" % (sub_range, s.ratio * s.ratio))
         return s
 
     def _workspace(self, shape, device):
@@ -185,7 +189,8 @@ class PointFlow(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, estimated_depth_map, interval, image_scale, it=0, *, feature_pyramids, cam_params_list,
-                mean, std, is_test=True, img_hw=None, pyramids_channels_last=None, out=None, interval_scale=1.0):
+                mean, std, is_test=True, img_hw=None, pyramids_channels_last=None, out=None, interval_scale=1.0,
+                sub_range=None):
         """One refinement iteration (model.py:150-295).
 
         estimated_depth_map [B,1,hp,wp]; interval [B] (= inter_scale * depth_interval,
@@ -193,8 +198,10 @@ class PointFlow(nn.Module):
         list returned by ``pyramids_to_channels_last`` via ``pyramids_channels_last``);
         cam_params_list [B,V,2,4,4]; mean/std [B,3].  ``interval_scale`` multiplies
         ``interval`` inside the kernels (lets the loop pass depth_interval and inter_scale
-        without a separate elementwise launch).  Returns (flow_result [B,1,h,w],
-        flow_prob [B,5,h,w])."""
+        without a separate elementwise launch).  ``sub_range=(first, count)`` processes only
+        those of the ratio^2 strided sub-clouds (the independent calls of model.py:236-267; used to
+        shard one view over GPUs, parallel.SubCloudShardedPass): only their pixels of the outputs are
+        written.  Returns (flow_result [B,1,h,w], flow_prob [B,5,h,w])."""
         require_cuda(estimated_depth_map, interval, cam_params_list, mean, std)
         if not self.training:
             # the reference runs inference under model.train() (test.py:58): BatchNorm uses batch
@@ -218,7 +225,8 @@ class PointFlow(nn.Module):
             img_hw = (pyr_hw[0][0] * 2, pyr_hw[0][1] * 2)  # conv1 is at half resolution (networks.py:84-124)
         depth = _lib.f32c(estimated_depth_map)
         self._validate(dev, B, V, pyr, depth, interval, mean, std, cam_params_list)
-        shape = self.make_shape(B, V, pyr_hw, tuple(depth.shape[2:]), img_hw, image_scale, is_test, interval_scale)
+        shape = self.make_shape(B, V, pyr_hw, tuple(depth.shape[2:]), img_hw, image_scale, is_test, interval_scale,
+                                sub_range)
         ws, need = self._workspace(shape, dev)
         w, _keep = self._weights(dev)
         track = self.update_running_stats and self.training
@@ -286,7 +294,7 @@ class PointFlow(nn.Module):
         shape, ws = self._last
         off = (C.c_size_t * 10)()
         check(lib.pmvs_point_flow_debug_offsets(C.byref(shape), C.byref(off)))
-        S = shape.ratio * shape.ratio
+        S = shape.sub_count if shape.sub_count > 0 else shape.ratio * shape.ratio
         hs, wsub = shape.flow_h // shape.ratio, shape.flow_w // shape.ratio
         N = 5 * hs * wsub
         R = S * shape.B * N

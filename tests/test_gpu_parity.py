@@ -531,6 +531,31 @@ def test_fetch_zero_padding_with_non_finite_features(golden_params, golden_weigh
     assert torch.allclose(feat[finite], want[finite], atol=3e-5, rtol=1e-5)
 
 
+def test_alternate_kernel_families_agree(golden_weights, golden_params):
+    """Every stage of the fused path exists in two kernel families (pmvs_set_option): the defaults and the
+    round-1 / generic kernels that the stand-alone operators and the unusual shapes still use.  Both must match the
+    oracle on the same iteration (and therefore each other)."""
+    from pointmvsnet_b200 import _lib
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    cpu = make_pointflow_inputs(64, 128, 4, 1, 48, seed=17)
+    saved = {k: _lib.get_option(k) for k in ("edge", "knn", "fetch", "gemm")}
+    outs = []
+    try:
+        for opts in (dict(edge=0, knn=0, fetch=0, gemm=0), dict(edge=1, knn=1, fetch=2, gemm=1), dict(saved)):
+            for k, v in opts.items():
+                _lib.set_option(k, v)
+            pf = _pf(golden_weights)
+            res, prob, stg, d_gpu, p_gpu = _run_iteration(pf, cpu, cpu["coarse_depth"], 0.25, 0.75, 1, golden_params)
+            _check_stages(pf, stg, 1)
+            assert torch.allclose(d_gpu, res, atol=5e-4, rtol=0), opts
+            assert torch.allclose(p_gpu, prob, atol=5e-5, rtol=0), opts
+            outs.append(d_gpu)
+    finally:
+        for k, v in saved.items():
+            _lib.set_option(k, v)
+    assert torch.allclose(outs[0], outs[2], atol=2e-4)
+
+
 def test_coarse_cost_volume_golden_and_oracle():
     """(f-1) plane-sweep fetch + variance: against the cost volume the reference forward fed to
     VolumeConv (every 6th plane, coarse_small.npz; tolerance 2e-5) and against the oracle on a

@@ -194,6 +194,11 @@ def test_bench_algorithmic_bytes_match_survey():
     assert abs(alg["fused_fetch"][0] / 1e6 - 409.5) < 1.0
     assert alg["fused_fetch"][1] == 3
     assert alg["knn3d"][0] == 537600 * 76
+    # the stage numerators of `roofline_stage` are SURVEY 8(d)'s: 409.5 MB fetch, 140 B/pt kNN (75 MB), 3 108 B/pt
+    # EdgeConv + MLP (1.67 GB) for one C2 pass
+    surv = bench.survey_8d_bytes_per_pass(512, 640, 4)
+    assert abs(surv["fetch"] / 1e6 - 409.5) < 1.0
+    assert surv["knn"] == 537600 * 140 and surv["edgeconv_mlp"] == 537600 * 3108
 
 
 def test_bench_per_iteration_grouping():
