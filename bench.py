@@ -576,6 +576,163 @@ def run_ours(args):
     return result_line
 
 
+def run_subcloud(args):
+    """BASELINE C5 style: ONE reference view refined by all ranks (parallel.SubCloudShardedPass): the view's
+    pyramids are owned per source view and all-gathered every step, iteration 1 is replicated, iterations 2 / 3 are
+    split by sub-cloud, the depth map is all-reduced after every split iteration.  A latency configuration (strong
+    scaling): value = iterations / time, NOT multiplied by the number of GPUs; bound 21 / (1 + 1 + 2) = 5.25x at 8."""
+    import torch.distributed as dist
+    from pointmvsnet_b200 import _lib
+    from pointmvsnet_b200.point_flow import PointFlow
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    from pointmvsnet_b200.parallel import SubCloudShardedPass, gather_view_pyramids, shard_views
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
+        dist.init_process_group("nccl", device_id=dev)
+    H, W, V, D = CONFIGS[args.config]
+    n_iter = len(IMG_SCALES)
+    host = make_pointflow_inputs(H, W, V, 1, D, seed=0, pin_memory=True)   # the same view on every rank
+    own = shard_views(V, rank, world)
+    host_own = [lv[:, own].contiguous().pin_memory() for lv in host["pyramids"]]
+    dev_own = [torch.empty_like(t, device=dev) for t in host_own]
+    small = {k: host[k].to(dev) for k in ("coarse_depth", "cam_params_list", "depth_interval", "mean", "std")}
+    pf = PointFlow().to(dev)
+    pf.load_reference_state_dict(load_pretrained_hot_path_weights())
+    pf.train()
+    sp = SubCloudShardedPass(pf, rank, world, IMG_SCALES, INTER_SCALES)
+    outs = [(torch.empty(1, 1, int(H * s), int(W * s), device=dev), torch.empty(1, 5, int(H * s), int(W * s), device=dev))
+            for s in IMG_SCALES]
+    host_out = torch.empty(1, 1, int(H * IMG_SCALES[-1]), int(W * IMG_SCALES[-1])).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(copy_in):
+        if copy_in:
+            for d, h in zip(dev_own, host_own):
+                d.copy_(h, non_blocking=True)
+        with torch.no_grad():
+            pyr = gather_view_pyramids(dev_own, V, rank, world)
+            cl = PointFlow.pyramids_to_channels_last(pyr)
+            depth = sp.run(cl, small["coarse_depth"], small["cam_params_list"], small["depth_interval"], small["mean"],
+                           small["std"], host["img_hw"], outs=outs)
+        if copy_in:
+            host_out.copy_(depth, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(nsteps, copy_in):
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0.0
+        for _ in range(nsteps):
+            barrier()
+            flush.zero_()
+            t0.record(stream)
+            step(copy_in)
+            t1.record(stream)
+            torch.cuda.synchronize(dev)
+            total += t0.elapsed_time(t1)
+        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / nsteps
+
+    for d, h in zip(dev_own, host_own):
+        d.copy_(h)
+    for _ in range(max(3, args.warmup)):
+        step(False)
+    n0 = _lib.launch_count()
+    step(False)
+    torch.cuda.synchronize(dev)
+    launches = _lib.launch_count() - n0
+    clk_p, clk_f = sample_clocks_start(local) if rank == 0 else (None, None)
+    ms = timed(args.steps, False)
+    clocks = sample_clocks_stop(clk_p, clk_f) if rank == 0 else None
+    e2e_ms = timed(args.steps, True)
+    line = None
+    if rank == 0:
+        h2d = sum(t.numel() * 4 for t in host_own)
+        line = json.dumps({
+            "metric": METRIC, "value": round(n_iter / (ms / 1e3), 2), "unit": "iters/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 5), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, H, W, V, D),
+                       "step": "ONE reference view per step refined by all %d GPU(s): pyramids owned per source view and "
+                               "all-gathered, iteration 1 replicated, iterations 2/3 split by sub-cloud (4 / 16 units), "
+                               "depth map all-reduced after each split iteration; eager launches (NCCL inside the step)" % world,
+                       "parallelism": "sub-cloud sharding over %d ranks (latency configuration, bound 5.25x at 8)" % world,
+                       "l2": "flushed before every step (256 MiB memset, untimed); per-step CUDA events, max over ranks",
+                       "weights": "pretrained hot-path weights of the reference (tests/golden/flow_weights.npz)"},
+            "e2e": {"value": round(n_iter / (e2e_ms / 1e3), 2), "unit": "iters/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": round(e2e_ms, 5),
+                    "how": "pinned host -> device copy of this rank's own views' pyramids, all-gather, pass, final "
+                           "depth map read back, all inside the timed region"},
+            "gpu_launches": int(launches * args.steps), "launches_per_step": int(launches), "clocks": clocks,
+        })
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def run_oplevel(args):
+    """The operator-level drop-in (an UNCHANGED reference model.py over this package's stand-alone operators,
+    pointmvsnet_b200/point_flow_oplevel.py): one reference view per step, eager launches, fp32 (TF32 off for the
+    stock flow_mlp convolutions).  Reported next to the fused path so that mode has a number."""
+    from pointmvsnet_b200 import _lib
+    from pointmvsnet_b200.point_flow import PointFlow
+    from pointmvsnet_b200.point_flow_oplevel import point_flow_pass_oplevel
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    rank, world, local = dist_env()
+    if rank != 0:
+        return None
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    H, W, V, D = CONFIGS[args.config]
+    inp = make_pointflow_inputs(H, W, V, 1, D, seed=0, device=dev)
+    pf = PointFlow().to(dev)
+    pf.load_reference_state_dict(load_pretrained_hot_path_weights())
+    pf.train()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        return point_flow_pass_oplevel(pf.flow_edge_conv, pf.flow_mlp, inp["coarse_depth"], inp["depth_interval"],
+                                       inp["pyramids"], inp["cam_params_list"], inp["mean"], inp["std"], inp["img_hw"])
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize(dev)
+    n0 = _lib.launch_count()
+    total = 0.0
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(args.steps):
+        flush.zero_()
+        t0.record()
+        step()
+        t1.record()
+        torch.cuda.synchronize(dev)
+        total += t0.elapsed_time(t1)
+    ms = total / args.steps
+    return json.dumps({
+        "metric": METRIC, "value": round(len(IMG_SCALES) / (ms / 1e3), 2), "unit": "iters/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, H, W, V, D), "mode": "oplevel",
+                   "step": "one reference view: the reference closure's control flow (21 cal_sub_flow calls) over the "
+                           "stand-alone operators, eager launches, device-resident inputs"},
+        "gpu_launches": int(_lib.launch_count() - n0),
+    })
+
+
 class _StdoutToStderr(object):
     """Route fd 1 to fd 2 while libraries (NCCL, CUDA, torchrun children) may chat; restore it
     for the single JSON line."""
@@ -603,12 +760,21 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--views-in-flight", type=int, default=2,
                     help="independent reference views whose passes run concurrently on one GPU (default 2)")
+    ap.add_argument("--mode", default="fused", choices=["fused", "oplevel"],
+                    help="fused: the PointFlow module (default); oplevel: the reference closure over the stand-alone "
+                         "operators (what an unchanged model.py runs)")
+    ap.add_argument("--parallel", default="views", choices=["views", "subcloud"],
+                    help="views: whole reference views per GPU (throughput, default); subcloud: all GPUs refine ONE "
+                         "view, iterations 2/3 split by sub-cloud (BASELINE C5, latency)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
         with _StdoutToStderr():
-            line = run_ours(args)
+            if args.mode == "oplevel":
+                line = run_oplevel(args)
+            else:
+                line = run_subcloud(args) if args.parallel == "subcloud" else run_ours(args)
         if line is not None:
             print(line, flush=True)
 

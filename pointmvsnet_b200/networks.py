@@ -40,9 +40,7 @@ def _edge_layer(mod, feature, knn_inds, concat_central):
         if ind.dtype != torch.int64:
             ind = ind.long()
         check(lib.pmvs_idx64_to_idx32(ptr(ind), ptr(idx32), ind.numel(), st))
-        w12 = torch.cat([mod.conv1.weight.detach()[:, :, 0], mod.conv2.weight.detach()[:, :, 0]], dim=0).float().contiguous()
-        gamma = mod.bn.weight.detach().float().contiguous()
-        beta = mod.bn.bias.detach().float().contiguous()
+        w12, gamma, beta = _layer_params(mod, dev)
         le = torch.empty(B * N, 2 * cout, device=dev, dtype=torch.float32)
         stats = torch.empty(4 * cout, device=dev, dtype=torch.float64)
         out_pm = torch.empty(B, N, ctot, device=dev, dtype=torch.float32)
@@ -64,6 +62,20 @@ def _edge_layer(mod, feature, knn_inds, concat_central):
         out = torch.empty(B, ctot, N, device=dev, dtype=torch.float32)
         check(lib.pmvs_transpose(ptr(out_pm), ptr(out), B, N, ctot, st))
     return out
+
+
+def _layer_params(mod, dev):
+    """[conv1.weight ; conv2.weight] stacked + BN affine, fp32 contiguous on `dev`; rebuilt only when a parameter
+    changed (21 calls per pass reuse them)."""
+    params = (mod.conv1.weight, mod.conv2.weight, mod.bn.weight, mod.bn.bias)
+    key = (str(dev),) + tuple((p.data_ptr(), p._version) for p in params)
+    cache = getattr(mod, "_pmvs_params", None)
+    if cache is None or cache[0] != key:
+        w12 = torch.cat([mod.conv1.weight.detach()[:, :, 0], mod.conv2.weight.detach()[:, :, 0]], dim=0)
+        vals = tuple(t.detach().to(device=dev, dtype=torch.float32).contiguous() for t in (w12, mod.bn.weight, mod.bn.bias))
+        cache = (key, vals)
+        object.__setattr__(mod, "_pmvs_params", cache)
+    return cache[1]
 
 
 def _update_running(bn, stats, cout, rows, K, concat_central):

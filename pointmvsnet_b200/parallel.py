@@ -42,6 +42,89 @@ def gather_ragged_depth_maps(local_depths, num_views):
     return torch.cat(parts, dim=0)
 
 
+def shard_sub_clouds(num_sub, rank, world):
+    """(first, count) of the sub-clouds of one iteration that `rank` processes: contiguous blocks in the
+    reference's (i, j) loop order (model.py:244-245); with fewer sub-clouds than ranks the high ranks idle
+    (count 0).  Iteration 1 has a single cloud, which every rank computes (replicated, no exchange)."""
+    if num_sub <= 1:
+        return 0, num_sub
+    ids = shard_views(num_sub, rank, world)
+    return (ids[0], len(ids)) if ids else (0, 0)
+
+
+def gather_view_pyramids(owned, num_views, rank, world):
+    """C5 'view-sharded' input: rank r owns the feature pyramids of the views
+    ``shard_views(num_views, r, world)`` (in the full system it ran ImageConv on those images); one
+    all-gather per level gives every rank all V views - 28*H*W bytes per view, far cheaper than exchanging
+    partial feature sums.  ``owned``: list over levels of [B, n_owned, C, h, w] (n_owned may be 0).
+    Returns the list over levels of [B, V, C, h, w]."""
+    if world == 1:
+        return owned
+    n_max = (num_views + world - 1) // world
+    out = []
+    for lvl in owned:
+        B, _, C, h, w = lvl.shape
+        slot = torch.zeros(B, n_max, C, h, w, dtype=lvl.dtype, device=lvl.device)
+        slot[:, :lvl.shape[1]] = lvl
+        slots = [torch.empty_like(slot) for _ in range(world)]
+        dist.all_gather(slots, slot)
+        parts = [slots[r][:, :len(shard_views(num_views, r, world))] for r in range(world)]
+        out.append(torch.cat(parts, dim=1).contiguous())
+    return out
+
+
+class SubCloudShardedPass(object):
+    """One reference view refined by `world` GPUs (BASELINE config C5; SURVEY.md 8e "sub-cloud units").
+
+    The ratio^2 strided sub-clouds of an iteration are independent calls in the reference
+    (model.py:236-267: own kNN graph, own BatchNorm batch statistics, own softmax), so they are the
+    units: iteration 1 (one cloud) is replicated on every rank, iteration 2 has 4 units, iteration 3
+    has 16.  After an iteration every rank holds the pixels of its own sub-clouds in an otherwise
+    zero depth map; one all-reduce(SUM) of that map (1.9 MB at C5) assembles the full map on every
+    rank - the only data-path collective, NCCL over NVLink.  Critical path 1 + 1 + 2 of the 21 units
+    at 8 ranks: a LATENCY configuration with a 5.25x bound, not the throughput one (that is whole
+    views per rank, bench.py default).  BatchNorm running statistics are not updated (each rank
+    sees only its sub-clouds; inference does not read them, test.py:58)."""
+
+    def __init__(self, point_flow, rank, world, img_scales=(0.125, 0.25, 0.5), inter_scales=(1.0, 0.75, 0.15)):
+        self.pf, self.rank, self.world = point_flow, rank, world
+        self.img_scales, self.inter_scales = tuple(img_scales), tuple(inter_scales)
+        point_flow.update_running_stats = False
+
+    def plan(self):
+        """[(first, count)] per iteration for this rank"""
+        from .point_flow import _ratio_for
+        return [shard_sub_clouds(_ratio_for(s, True) ** 2, self.rank, self.world) for s in self.img_scales]
+
+    def run(self, pyramids_cl, coarse_depth, cam_params_list, depth_interval, mean, std, img_hw, outs=None):
+        """pyramids_cl: channels-last levels of ALL views (PointFlow.pyramids_to_channels_last of the
+        gathered pyramids).  Returns the final [B,1,h,w] depth map (identical on every rank)."""
+        depth = coarse_depth
+        B = coarse_depth.shape[0]
+        for i, (s, isc) in enumerate(zip(self.img_scales, self.inter_scales)):
+            first, count = self.plan()[i]
+            h, w = int(img_hw[0] * s), int(img_hw[1] * s)
+            d_out, p_out = outs[i] if outs is not None else (
+                torch.empty(B, 1, h, w, device=depth.device), torch.empty(B, 5, h, w, device=depth.device))
+            sharded = _num_sub(s) > 1 and self.world > 1
+            if sharded:
+                d_out.zero_()
+            if count > 0:
+                self.pf(depth, depth_interval, s, i, interval_scale=isc, feature_pyramids=None,
+                        cam_params_list=cam_params_list, mean=mean, std=std, is_test=True, img_hw=img_hw,
+                        pyramids_channels_last=pyramids_cl, out=(d_out, p_out),
+                        sub_range=(first, count) if sharded else None)
+            if sharded:
+                dist.all_reduce(d_out)  # disjoint supports: the sum assembles the map
+            depth = d_out
+        return depth
+
+
+def _num_sub(scale):
+    from .point_flow import _ratio_for
+    return _ratio_for(scale, True) ** 2
+
+
 def state_dict_from_params(params, template):
     """Flat oracle-style parameter dict (synthetic.make_flow_params) -> state_dict with the
     reference's key names; running statistics come from ``template``."""

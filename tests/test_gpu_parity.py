@@ -531,6 +531,69 @@ def test_fetch_zero_padding_with_non_finite_features(golden_params, golden_weigh
     assert torch.allclose(feat[finite], want[finite], atol=3e-5, rtol=1e-5)
 
 
+def test_sub_cloud_range_equals_the_same_pixels_of_the_full_iteration(golden_weights):
+    """pmvs_flow_shape.sub_begin / sub_count (the unit of the C5 multi-GPU split): processing sub-clouds
+    [first, first + count) alone writes exactly the pixels (and probabilities) the full iteration writes there -
+    sub-clouds are independent calls in the reference (model.py:236-267) - and leaves the others untouched."""
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    cpu = make_pointflow_inputs(128, 192, 3, 2, 48, seed=23)
+    pf = _pf(golden_weights)
+    pf.update_running_stats = False
+    args = dict(feature_pyramids=[p.to(DEV) for p in cpu["pyramids"]], cam_params_list=cpu["cam_params_list"].to(DEV),
+                mean=cpu["mean"].to(DEV), std=cpu["std"].to(DEV), img_hw=cpu["img_hw"])
+    with torch.no_grad():
+        d1, _ = pf(cpu["coarse_depth"].to(DEV), cpu["depth_interval"].to(DEV), 0.125, 0, **args)
+        for scale, isc, it in ((0.25, 0.75, 1), (0.5, 0.15, 2)):
+            full_d, full_p = pf(d1, (isc * cpu["depth_interval"]).to(DEV), scale, it, **args)
+            full_d, full_p = full_d.clone(), full_p.clone()
+            r = int(scale * 8)
+            for first, count in ((0, 1), (1, r * r - 1), (r * r - 1, 1)):
+                out_d = torch.full_like(full_d, -7.0)
+                out_p = torch.full_like(full_p, -7.0)
+                pf(d1, (isc * cpu["depth_interval"]).to(DEV), scale, it, out=(out_d, out_p), sub_range=(first, count), **args)
+                torch.cuda.synchronize()
+                mask = torch.zeros(r, r, dtype=torch.bool)
+                mask.view(-1)[first:first + count] = True
+                h, w = full_d.shape[-2:]
+                pix = mask.to(DEV).repeat(h // r, w // r)  # pixel (Y, X) belongs to sub-cloud (Y % r, X % r)
+                # (fp64 atomics make the BatchNorm sums order dependent in the last bit, hence not torch.equal)
+                assert torch.allclose(out_d[:, 0][:, pix], full_d[:, 0][:, pix], atol=2e-4, rtol=0)
+                assert torch.allclose(out_p[:, :, pix], full_p[:, :, pix], atol=1e-5, rtol=0)
+                assert (out_d[:, 0][:, ~pix] == -7.0).all() and (out_p[:, :, ~pix] == -7.0).all()
+                assert pf.debug_stages()["S"] == count
+
+
+def test_oplevel_closure_equals_fused_point_flow(golden_weights):
+    """The UNCHANGED-model.py mode: the reference closure's control flow (21 cal_sub_flow calls per pass) over the
+    stand-alone operators (FeatureFetcher, get_knn_3d, EdgeConvNoC / EdgeConv kernels; flow_mlp = stock fp32 PyTorch)
+    reproduces the fused PointFlow pass on the golden inputs of the reference forward."""
+    from pointmvsnet_b200.point_flow import PointFlowPass
+    from pointmvsnet_b200.point_flow_oplevel import point_flow_pass_oplevel
+    gp = load_golden("pass_small.npz")
+    H, W = [int(v) for v in gp["img_hw"]]
+    interval = gp["cams"][:, 0, 1, 3, 1].to(DEV)
+    pyr = [gp[k].to(DEV) for k in ("conv1", "conv2", "conv3")]
+    pf = _pf(golden_weights)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            fused = PointFlowPass(pf).run(pyr, gp["coarse_depth"].to(DEV), gp["cams"].to(DEV), interval,
+                                          gp["mean"].to(DEV), gp["std"].to(DEV), (H, W))
+            fused = [(d.clone(), p.clone()) for d, p in fused]
+            ops = point_flow_pass_oplevel(pf.flow_edge_conv, pf.flow_mlp, gp["coarse_depth"].to(DEV), interval, pyr,
+                                          gp["cams"].to(DEV), gp["mean"].to(DEV), gp["std"].to(DEV), (H, W))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    for i, ((df, pfp), (do, po), isc) in enumerate(zip(fused, ops, (1.0, 0.75, 0.15))):
+        err = (df - do).abs().flatten()
+        itv = float(interval[0]) * isc
+        # chained iterations: the same statistical bound as the fused pass against the oracle
+        assert err.mean() <= 1e-4 * itv and torch.quantile(err, 0.999) <= 1e-3 * itv, (i, err.mean(), err.max())
+        assert (pfp - po).abs().mean() < 1e-4
+
+
 def test_alternate_kernel_families_agree(golden_weights, golden_params):
     """Every stage of the fused path exists in two kernel families (pmvs_set_option): the defaults and the
     round-1 / generic kernels that the stand-alone operators and the unusual shapes still use.  Both must match the

@@ -156,7 +156,7 @@ def test_shard_views_partition():
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %r)
-from pointmvsnet_b200.parallel import shard_views, gather_depth_maps, gather_ragged_depth_maps
+from pointmvsnet_b200.parallel import shard_views, gather_depth_maps, gather_ragged_depth_maps, gather_view_pyramids
 dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
 views = 5
@@ -167,6 +167,13 @@ assert full.shape == (views, 1, 4, 6)
 assert torch.equal(full[:, 0, 0, 0], torch.arange(views, dtype=torch.float32)), full[:, 0, 0, 0]
 eq = gather_depth_maps(torch.full((1, 1, 4, 6), float(rank)))
 assert [t[0, 0, 0, 0].item() for t in eq] == [float(r) for r in range(world)]
+# C5 view-sharded input: every rank owns some views' pyramids, one all-gather per level gives everyone all V
+V = 5
+g = torch.Generator().manual_seed(3)
+full_pyr = [torch.randn(1, V, c, 4, 6, generator=g) for c in (16, 32, 64)]
+own = shard_views(V, rank, world)
+got = gather_view_pyramids([lv[:, own] for lv in full_pyr], V, rank, world)
+assert all(torch.equal(a, b) for a, b in zip(got, full_pyr))
 dist.barrier()
 dist.destroy_process_group()
 print("OK", rank)
@@ -184,6 +191,22 @@ def test_depth_map_gather_world_size_2_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0 and "OK" in out, out
+
+
+def test_sub_cloud_partition_covers_every_unit_once():
+    """C5 partition: 1 / 4 / 16 sub-clouds over 1, 2, 4, 8 ranks - every sub-cloud exactly once,
+    contiguous blocks, iteration 1 replicated; the 8-rank critical path is 1 + 1 + 2 units."""
+    from pointmvsnet_b200.parallel import shard_sub_clouds
+    for world in (1, 2, 4, 8):
+        for S in (4, 16):
+            owned = []
+            for r in range(world):
+                first, count = shard_sub_clouds(S, r, world)
+                owned += list(range(first, first + count))
+            assert sorted(owned) == list(range(S))
+        assert all(shard_sub_clouds(1, r, world) == (0, 1) for r in range(world))
+    assert max(shard_sub_clouds(16, r, 8)[1] for r in range(8)) == 2
+    assert max(shard_sub_clouds(4, r, 8)[1] for r in range(8)) == 1
 
 
 def test_bench_algorithmic_bytes_match_survey():
