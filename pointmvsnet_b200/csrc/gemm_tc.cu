@@ -345,16 +345,8 @@ static int g_mode = 3;  // 0: SIMT fp32 GEMM, 1: TF32 tensor cores, 3: 3xTF32 te
 template <int N_OUT, int NSPLIT>
 static int launch_one(const GemmArgs& a, cudaStream_t st, const char* name) {
   using S = Smem<N_OUT, NSPLIT>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<N_OUT, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
-        cudaSuccess) {
-      cudaGetLastError();
-      set_error("gemm_tc: cannot reserve %d bytes of shared memory", S::TOTAL);
-      return PMVS_ERR_CUDA;
-    }
-    configured = true;
-  }
+  static unsigned long long smem_done = 0;  // per device: the attribute belongs to the device's context
+  PMVS_TRY((ensure_dyn_smem(gemm_tc_kernel<N_OUT, NSPLIT>, S::TOTAL, smem_done, "gemm_tc")));
   dim3 grid(cdiv(a.rows_per_group, BM), a.groups);
   prof_begin(name, st);
   gemm_tc_kernel<N_OUT, NSPLIT><<<grid, NUM_THREADS, S::TOTAL, st>>>(a);
