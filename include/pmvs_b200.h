@@ -62,8 +62,8 @@ int pmvs_get_gemm_mode(void);
  *   PMVS_OPT_FETCH  1 = consecutive hypotheses share the texel quad, packed fp32 math (3 CTAs / SM),
  *                   2 = the same with 2 CTAs / SM and no register spills, 0 = 4 taps per (hypothesis, view)
  *                   (the kernel used for V > 6)
- *   PMVS_OPT_GEMM   2 = weights in tensor memory, points as N, persistent, cp.async staging 5 chunks deep,
- *                   3 = 6 chunks deep, 1 = the same kernel with register prefetch (4 chunks),
+ *   PMVS_OPT_GEMM   2 = weights in tensor memory, points as N, persistent, cp.async staging ring (4 chunks in
+ *                   flight), 1 = the same kernel with register prefetch,
  *                   0 = points-as-M with shared-memory operands (the kernel plain-TF32 mode uses)
  *   PMVS_OPT_DEBUG_IDX  1 = also materialise int32 neighbour indices in the workspace */
 #define PMVS_OPT_EDGE 1

@@ -51,9 +51,9 @@ constexpr int A_LD = NT * 8 / PROD_THREADS;   // float4 loads per producer threa
 // ring.  ASYNC = N > 0: the raw fp32 chunks travel global -> shared memory with cp.async (LDGSTS, no registers
 // held) into an N-stage staging ring, N - 1 chunks ahead; the producer converts its own pieces from there into a
 // 2-stage operand ring.  16 KB per staging stage, 32 KB per operand stage (X_hi | X_lo).
-template <int ASYNC>
+template <int ASYNC, int NSTAGES>
 struct Layout {
-  static constexpr int NST = ASYNC > 0 ? 2 : 4;  // operand stages
+  static constexpr int NST = NSTAGES;  // operand stages
   static constexpr int RING = 0;
   static constexpr int STAGING = RING + NST * STAGE_BYTES;
   static constexpr int XBUF = STAGING + ASYNC * PLANE_BYTES;
@@ -155,9 +155,9 @@ __device__ __forceinline__ TileRange my_tiles(int total) {
   return TileRange{lo, hi - lo};
 }
 
-template <int COUT, bool IN_BN, int ASYNC>
+template <int COUT, bool IN_BN, int ASYNC, int NSTAGES>
 __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
-  using LY = Layout<ASYNC>;
+  using LY = Layout<ASYNC, NSTAGES>;
   constexpr int STAGES = LY::NST;
   constexpr int SM_RING = LY::RING, SM_STAGING = LY::STAGING, SM_XBUF = LY::XBUF, SM_BN = LY::BN, SM_BAR = LY::BAR;
   constexpr int PF = ASYNC > 0 ? ASYNC - 1 : 4;  // chunks of global loads in flight per producer thread
@@ -412,9 +412,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
         for (int c = 0; c < nch; ++c, ++n) {
           const int stage = n % STAGES;
           mbar_wait(bar_full(stage), (uint32_t)((n / STAGES) & 1));
-          fence_proxy_async();  // the producers' generic-proxy stores (acquired above) -> the tensor core's async proxy
-          tc_fence_after();
           if (lane == 0) {
+            fence_proxy_async();  // the producers' generic-proxy stores (acquired above) -> the tensor core's async proxy
+            tc_fence_after();
             const uint32_t x_hi = smem_base + SM_RING + stage * STAGE_BYTES, x_lo = x_hi + PLANE_BYTES;
             const int ksteps = min(KC, K - c * KC) / 8;
             for (int j = 0; j < ksteps; ++j) {
@@ -570,11 +570,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
   }
 }
 
-template <int COUT, bool IN_BN, int ASYNC>
+template <int COUT, bool IN_BN, int ASYNC, int NSTAGES>
 static int launch_pf(const GemmArgs& a, cudaStream_t st, const char* name) {
-  constexpr int SM_TOTAL = Layout<ASYNC>::TOTAL;
+  constexpr int SM_TOTAL = Layout<ASYNC, NSTAGES>::TOTAL;
   static unsigned long long smem_done = 0;
-  PMVS_TRY((ensure_dyn_smem(gemm_ws_kernel<COUT, IN_BN, ASYNC>, SM_TOTAL, smem_done, "gemm_ws")));
+  PMVS_TRY((ensure_dyn_smem(gemm_ws_kernel<COUT, IN_BN, ASYNC, NSTAGES>, SM_TOTAL, smem_done, "gemm_ws")));
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -584,16 +584,16 @@ static int launch_pf(const GemmArgs& a, cudaStream_t st, const char* name) {
   const long long tiles = (long long)a.groups * cdiv(a.rows_per_group, NT);
   const int grid = (int)std::min<long long>(tiles, num_sms);
   prof_begin(name, st);
-  gemm_ws_kernel<COUT, IN_BN, ASYNC><<<grid, THREADS, SM_TOTAL, st>>>(a);
+  gemm_ws_kernel<COUT, IN_BN, ASYNC, NSTAGES><<<grid, THREADS, SM_TOTAL, st>>>(a);
   return check_launch("gemm_ws_kernel", st);
 }
 template <int COUT, bool IN_BN>
 static int launch_one(const GemmArgs& a, cudaStream_t st, const char* name) {
-  switch (opt(OPT_GEMM)) {
-    case 2: return launch_pf<COUT, IN_BN, 6>(a, st, name);  // cp.async staging ring, 5 chunks (80 KB) in flight
-    case 3: return launch_pf<COUT, IN_BN, 7>(a, st, name);  // 6 chunks (96 KB) in flight
-  }
-  return launch_pf<COUT, IN_BN, 0>(a, st, name);            // register prefetch, 4 chunks (64 KB) in flight
+  // Depth variants measured within 1 % of each other at BASELINE C2 (staging 3..7 stages x operand 2..4 stages, round 2):
+  // the kernels sit at ~70 % of what a read-dominated stream reaches on this part (profiles/r02/hbm_read_probe.txt),
+  // not at a pipeline-depth limit.  Two are kept: the default and the register-prefetch form.
+  if (opt(OPT_GEMM) == 1) return launch_pf<COUT, IN_BN, 0, 4>(a, st, name);  // register prefetch, 4 chunks in flight, 4 operand stages
+  return launch_pf<COUT, IN_BN, 5, 3>(a, st, name);  // cp.async staging: 4 chunks (64 KB) in flight, 3 operand stages
 }
 
 }  // namespace ws
