@@ -226,8 +226,9 @@ int pmvs_pyramid_to_channels_last(const float* nchw, float* nhwc, int BV, int C,
  * tests to compare every stage with the oracle).  Returns byte offsets into workspace:
  * off[0]=feature [S,B,N,136], off[1]=xyz [S,B,3,N], off[2]=idx32 [S,B,N,16] (valid if off[9]),
  * off[3]=edge cat [S,B,N,224], off[4]=mlp h2 [S,B,N,16], off[5]=LE scratch, off[6]=BN sums,
- * off[7]=total bytes, off[8]=kNN candidate ids [S,B,N,16] uint8 (id = d*25+h*5+w of the 5x5x5
- * window, bit 7 = candidate outside the grid), off[9]=1 if idx32 was materialised;
+ * off[7]=total bytes, off[8]=kNN neighbour codes [S,B,N,16] uint16 (inside the grid: (dd+2)*96 +
+ * (dh+2)*12 + (dw+2), the row offset in the EdgeConv halo tile; outside: bit 15 + candidate id
+ * d*25+h*5+w of the 5x5x5 window), off[9]=1 if idx32 was materialised;
  * S = ratio^2, N = 5*h'*w'. */
 int pmvs_point_flow_debug_offsets(const pmvs_flow_shape* shape, size_t off[10]);
 

@@ -140,7 +140,7 @@ struct FlowPlan {
   size_t R;  // rows = S * B * N
   size_t cam, feature, xyz, idx, le, ecat, h0, h1, h2, stats, total;
   size_t warp_src;     // the pyramid levels resized to the flow grid, [B,V,h,w,112]
-  size_t cand;         // [R, 16] bytes: kNN candidate ids for the tile EdgeConv kernels
+  size_t cand;         // [R, 16] uint16: kNN neighbour codes for the tile EdgeConv kernels
   // offsets (in doubles) inside the stats region.  Per EdgeConv layer and group 6*cout doubles: st_ec = 4*cout
   // (gather path: [sum_c | sumsq_c | sum_n | sumsq_n]; tile path: column sums / sums of squares of the
   // 2*cout GEMM outputs), st_ecn = 2*cout ([sum_n | sumsq_n] of the tile path)
@@ -183,7 +183,7 @@ static int make_plan(const pmvs_flow_shape* s, FlowPlan& p) {
   p.h1 = o; o += align_up(p.R * 64 * 4);
   p.h2 = o; o += align_up(p.R * 16 * 4);
   p.warp_src = o; o += align_up(warp_source_bytes(s->B, s->V, s->flow_h, s->flow_w));
-  p.cand = o; o += align_up(p.R * PMVS_KNN);
+  p.cand = o; o += align_up(p.R * PMVS_KNN * 2);
   size_t d = 0;
   const int ec_cout[3] = {32, 32, 64};
   const int mlp_cout[3] = {64, 64, 16};
@@ -397,7 +397,7 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
   // a10: neighbour lists.  The tile EdgeConv path consumes 1-byte candidate ids; the int32 row indices are only
   // materialised for the gather path (or on request, for the tests)
   const int edge_impl = opt(OPT_EDGE);
-  unsigned char* cand = (unsigned char*)(ws + p.cand);
+  unsigned short* cand = (unsigned short*)(ws + p.cand);
   if (edge_impl != 0)
     PMVS_TRY(launch_knn3d_cand(xyz, opt(OPT_DEBUG_IDX) ? idx : nullptr, cand, S * B, PMVS_NUM_HYP, p.hs, p.ws, st));
   else

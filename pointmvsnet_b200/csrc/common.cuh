@@ -125,9 +125,10 @@ __device__ __forceinline__ float bn_apply(float x, float mean, float invstd, flo
 }
 
 // ---- internal launchers shared between translation units ---------------------------
-// knn3d of the fused path (ksize 5, knn 16): 1-byte candidate ids [clouds*D*H*W, 16] (bit 7 set = the candidate lies
-// outside the grid, torch_utils.py:44,51-59) and, optionally (idx32 != NULL), the int32 linear indices
-int launch_knn3d_cand(const float* xyz, int32_t* idx32, unsigned char* cand, int clouds, int D, int H, int W,
+// knn3d of the fused path (ksize 5, knn 16): 16-bit neighbour codes [clouds*D*H*W, 16] (knn3d.cu knn_code16: halo-tile
+// row offset, or bit 15 + candidate id for a candidate outside the grid, torch_utils.py:44,51-59) and, optionally
+// (idx32 != NULL), the int32 linear indices
+int launch_knn3d_cand(const float* xyz, int32_t* idx32, unsigned short* cand, int clouds, int D, int H, int W,
                       cudaStream_t st);
 int launch_knn3d(const float* xyz, int64_t* idx64, int32_t* idx32, int clouds, int D, int H, int W,
                  int ksize, int knn, cudaStream_t st);
@@ -174,7 +175,7 @@ int launch_edge_apply(const EdgeArgs& a, cudaStream_t st);
 // shared-memory halo tile (edge_tile.cu)
 struct EdgeTileArgs {
   const float* le;            // [R, 2*cout]  (local | edge), R = groups * clouds_per_group * 5 * gh * gw
-  const unsigned char* cand;  // [R, 16] candidate ids from launch_knn3d_cand
+  const unsigned short* cand;  // [R, 16] neighbour codes from launch_knn3d_cand
   const double* cstats;       // per group [sum(2*cout) | sumsq(2*cout)] of the LE columns (GEMM epilogue)
   double* nstats;             // per group [sum_n(cout) | sumsq_n(cout)] of edge[idx] - local over (rows, K)
   float* coef;                // per group 6*cout floats: BatchNorm coefficients, written by the last statistics CTA

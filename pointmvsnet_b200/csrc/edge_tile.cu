@@ -9,11 +9,11 @@
 // matrix LE[R, 2*cout] seen as the 4-D tensor (channel, x, y, cloud*5 + layer) - arrives with ONE
 // cp.async.bulk.tensor.4d (TMA, SASS UTMALDG) completing on an mbarrier; coordinates outside the
 // grid are zero-filled by the TMA unit.  Neighbour k of a point is then one LDS.128 at
-// base(point) + lut[candidate id], the 1-byte candidate id (d*25 + h*5 + w, torch_utils.py:32-38) being
-// what the kNN kernel emits instead of 4/8-byte row indices.  A pick that lies OUTSIDE the grid (the
-// zero-vector candidates of torch_utils.py:44, whose clamped / row-wrapped linear index aliases some
-// other row, :51-59; 0.04 % of the picks) carries bit 7 and is fetched from global memory at exactly
-// that aliased row.  Several CTAs are resident per SM, so one CTA's TMA wait overlaps the others' math.
+// base(point) + 128 * code, the 16-bit code being what the kNN kernel emits instead of 4/8-byte row indices:
+// the row offset (dd+2)*96 + (dh+2)*12 + (dw+2) inside this very tile geometry (knn3d.cu knn_code16) - no
+// look-up table, one shift-add per gather.  A pick that lies OUTSIDE the grid (the zero-vector candidates
+// of torch_utils.py:44, whose clamped / row-wrapped linear index aliases some other row, :51-59; 0.04 % of
+// the picks) carries bit 15 + the candidate id and is fetched from global memory at exactly that aliased row.  Several CTAs are resident per SM, so one CTA's TMA wait overlaps the others' math.
 //
 // Arithmetic is edge_kernel's (edgeconv.cu), on fp32 pairs (FFMA2 / FADD2): statistics d = e - l,
 // s1 += d, s2 = fma(d, d, s2); apply fma(e, A, c0) with A = istd * gamma, c0 = beta - (mean + l) * A.
@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(ET_THREADS, 3) edge_tile_kernel(const __grid_c
   constexpr int LD = 2 * COUT;
   constexpr int SLABS = COUT / ET_CP;
   constexpr int STEPS = G::NPTS / (ET_WARPS * ET_PPW);  // points per thread
+  static_assert(G::HX == 12 && G::HY == 8, "the kNN kernel's 16-bit codes are row offsets of a 12 x 8 x 5 halo tile");
   extern __shared__ __align__(128) float halo[];  // [ROWS][32], filled by the TMA
-  __shared__ int lut[128];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ float part[APPLY ? 1 : ET_WARPS][APPLY ? 1 : 2 * ET_CP];
   __shared__ __align__(16) float coef[APPLY ? ET_COEF * COUT : 4];
@@ -97,16 +97,13 @@ __global__ void __launch_bounds__(ET_THREADS, 3) edge_tile_kernel(const __grid_c
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 125) lut[tid] = (((tid / 25 - 2) * G::HY + ((tid % 25) / 5 - 2)) * G::HX + (tid % 5 - 2)) * ET_CP;
   if (APPLY) {
     const float* cg = a.coef + (size_t)g * ET_COEF * COUT;
     for (int c = tid; c < ET_COEF * COUT; c += ET_THREADS) coef[c] = __ldg(cg + c);
   }
 
-  // the points of this thread (fixed for the CTA): candidate ids (16 bytes per point) are fetched once, before
-  // the tile arrives, so that their latency overlaps the TMA's
+  // the points of this thread (fixed for the CTA)
   int pn[STEPS], pbase[STEPS];
-  uint4 cw[STEPS];
 #pragma unroll
   for (int s = 0; s < STEPS; ++s) {
     const int it = s * (ET_WARPS * ET_PPW) + warp * ET_PPW + sub;
@@ -115,10 +112,18 @@ __global__ void __launch_bounds__(ET_THREADS, 3) edge_tile_kernel(const __grid_c
     const int y = y0 + ty, x = x0 + tx;
     const bool ok = y < gh && x < gw;
     pn[s] = ok ? (d * gh + y) * gw + x : -1;
-    pbase[s] = ((d * G::HY + ty + 2) * G::HX + tx + 2) * ET_CP + cl;
-    cw[s] = ok ? __ldg(reinterpret_cast<const uint4*>(a.cand + (cloud_base + (size_t)pn[s]) * PMVS_KNN))
-               : make_uint4(0u, 0u, 0u, 0u);
+    // row of candidate code 0 = offset (-2, -2, -2) from the point, in floats (may be negative for d < 2)
+    pbase[s] = (((d - 2) * G::HY + ty) * G::HX + tx) * ET_CP + cl;
   }
+  auto load_codes = [&](int s, uint4& c0, uint4& c1) {  // 16 x 16-bit neighbour codes of point s
+    if (pn[s] >= 0) {
+      const uint4* cp = reinterpret_cast<const uint4*>(a.cand + (cloud_base + (size_t)pn[s]) * PMVS_KNN);
+      c0 = __ldg(cp);
+      c1 = __ldg(cp + 1);
+    } else {
+      c0 = c1 = make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
   __syncthreads();
 
 #pragma unroll 1
@@ -154,14 +159,17 @@ __global__ void __launch_bounds__(ET_THREADS, 3) edge_tile_kernel(const __grid_c
     }
 
     f32x2 n1_lo = pack2(0.f, 0.f), n1_hi = n1_lo, n2_lo = n1_lo, n2_hi = n1_lo;
+    uint4 nx0, nx1;  // codes of the next point: in flight while the current one is processed
+    load_codes(0, nx0, nx1);
 #pragma unroll
     for (int s = 0; s < STEPS; ++s) {
+      const uint4 ca = nx0, cb = nx1;
+      if (s + 1 < STEPS) load_codes(s + 1, nx0, nx1);
       if (pn[s] < 0) continue;
       const int n = pn[s];
       const size_t row = cloud_base + (size_t)n;
       const float4 lc = loc[s];
-      const uint4 cws = cw[s];
-      const bool esc = ((cws.x | cws.y | cws.z | cws.w) & 0x80808080u) != 0u;
+      const bool esc = ((ca.x | ca.y | ca.z | ca.w | cb.x | cb.y | cb.z | cb.w) & 0x80008000u) != 0u;
       const float* hbase = halo + pbase[s];
       f32x2 A_lo = 0ull, A_hi = 0ull, c_lo = 0ull, c_hi = 0ull, o_lo = pack2(0.f, 0.f), o_hi = o_lo;
       const f32x2 l_lo = pack2(lc.x, lc.y), l_hi = pack2(lc.z, lc.w);
@@ -187,29 +195,28 @@ __global__ void __launch_bounds__(ET_THREADS, 3) edge_tile_kernel(const __grid_c
           n2_lo = fma2(d_lo, d_lo, n2_lo); n2_hi = fma2(d_hi, d_hi, n2_hi);
         }
       };
-      auto cand_of = [&](int k) -> unsigned {  // no indexable array: that would live in local memory
-        const unsigned wd = k < 4 ? cws.x : (k < 8 ? cws.y : (k < 12 ? cws.z : cws.w));
-        return (wd >> (8 * (k & 3))) & 255u;
+      auto code_of = [&](int k) -> unsigned {  // no indexable array: that would live in local memory
+        const int wq = k >> 1;
+        const unsigned wd = wq == 0 ? ca.x : wq == 1 ? ca.y : wq == 2 ? ca.z : wq == 3 ? ca.w
+                          : wq == 4 ? cb.x : wq == 5 ? cb.y : wq == 6 ? cb.z : cb.w;
+        return (k & 1) ? wd >> 16 : wd & 0xffffu;
       };
       if (!esc) {
-        // 16 independent table look-ups first, then 16 independent 128-bit gathers: no dependent LDS chain per pick
-        int off[PMVS_KNN];
+        // 16 independent 128-bit gathers: row = base + code, i.e. one shift-add per address
 #pragma unroll
-        for (int k = 0; k < PMVS_KNN; ++k) off[k] = lut[cand_of(k)];
-#pragma unroll
-        for (int k = 0; k < PMVS_KNN; ++k) body(*reinterpret_cast<const float4*>(hbase + off[k]));
+        for (int k = 0; k < PMVS_KNN; ++k) body(*reinterpret_cast<const float4*>(hbase + code_of(k) * ET_CP));
       } else {
 #pragma unroll 1
         for (int k = 0; k < PMVS_KNN; ++k) {
-          const unsigned c = cand_of(k);
-          if (c & 128u) {
+          const unsigned c = code_of(k);
+          if (c & 0x8000u) {
             // out-of-grid candidate: the reference gathers row clamp(n + dd*HW + dh*W + dw) (torch_utils.py:51-59)
             const int j = (int)(c & 127u);
             int t = n + (j / 25 - 2) * HW + ((j % 25) / 5 - 2) * gw + (j % 5 - 2);
             t = t < 0 ? 0 : (t > N - 1 ? N - 1 : t);
             body(ldg4(a.le + (cloud_base + (size_t)t) * LD + COUT + ch0 + cl));
           } else {
-            body(*reinterpret_cast<const float4*>(hbase + lut[c]));
+            body(*reinterpret_cast<const float4*>(hbase + c * ET_CP));
           }
         }
       }

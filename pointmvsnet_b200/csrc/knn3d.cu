@@ -51,11 +51,18 @@ __constant__ signed char c_ring5[25][2] = {{0, 0},  {-1, 0},  {0, -1}, {0, 1},  
                                            {1, 2},  {2, -1},  {2, 1},  {-2, -2}, {-2, 2}, {2, -2},  {2, 2}};
 __constant__ signed char c_ring3[9][2] = {{0, 0}, {-1, 0}, {0, -1}, {0, 1}, {1, 0}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
 
+// 16-bit neighbour code consumed by the tile EdgeConv kernels (edge_tile.cu): for a candidate inside the grid the
+// row offset (dd+2)*96 + (dh+2)*12 + (dw+2) inside an (8+4) x (4+4) x 5 halo tile, so that the gather address is one
+// shift-add; for a candidate OUTSIDE the grid (zero-vector candidate, torch_utils.py:44) bit 15 and the candidate id.
+__device__ __forceinline__ unsigned knn_code16(unsigned fd, unsigned fh, unsigned fw, unsigned id, bool in_grid) {
+  return in_grid ? fd * 96u + fh * 12u + fw : (0x8000u | id);
+}
+
 // picks -> linear indices with the reference's global clamp (torch_utils.py:51-59), plus (optional)
-// the 1-byte candidate ids the tile EdgeConv kernels consume: bit 7 marks a candidate OUTSIDE the grid
+// the 16-bit neighbour codes the tile EdgeConv kernels consume
 template <int KS, int K, typename IdxT>
 __device__ __forceinline__ void knn_emit(const int (&bi)[K], IdxT* __restrict__ idx_out,
-                                         unsigned char* __restrict__ cand_out, long long point, long long n,
+                                         unsigned short* __restrict__ cand_out, long long point, long long n,
                                          int x, int y, int z, int D, int H, int W) {
   constexpr int HK = KS / 2;
   const long long HW = (long long)H * W, DHW = HW * D;
@@ -77,22 +84,24 @@ __device__ __forceinline__ void knn_emit(const int (&bi)[K], IdxT* __restrict__ 
     for (int p = 0; p < K; p += VEC) *reinterpret_cast<int4*>(dst + p) = *reinterpret_cast<const int4*>(&vals[p]);
   }
   if (K == 16 && KS == 5 && cand_out != nullptr) {
-    unsigned w4[4] = {0u, 0u, 0u, 0u};
+    unsigned w8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
     for (int p = 0; p < K; ++p) {
       const int j = bi[p];
       const int od = j / (KS * KS) - HK, oh = (j % (KS * KS)) / KS - HK, ow = j % KS - HK;
       const bool in = z + od >= 0 && z + od < D && y + oh >= 0 && y + oh < H && x + ow >= 0 && x + ow < W;
-      w4[p >> 2] |= ((unsigned)j | (in ? 0u : 128u)) << (8 * (p & 3));
+      w8[p >> 1] |= knn_code16((unsigned)(od + HK), (unsigned)(oh + HK), (unsigned)(ow + HK), (unsigned)j, in) << (16 * (p & 1));
     }
-    *reinterpret_cast<uint4*>(cand_out + point * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    uint4* dst = reinterpret_cast<uint4*>(cand_out + point * 16);
+    dst[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+    dst[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
   }
 }
 
 template <int KS, int K, typename IdxT>
 __global__ void __launch_bounds__(KNN_TX* KNN_TY* KNN_TD)
     knn3d_kernel(const float* __restrict__ xyz, IdxT* __restrict__ idx_out, int D, int H, int W, int dtiles,
-                 unsigned char* __restrict__ cand_out) {
+                 unsigned short* __restrict__ cand_out) {
   constexpr int HK = KS / 2;
   constexpr int SX = KNN_TX + 2 * HK, SY = KNN_TY + 2 * HK, SZ = KNN_TD + 2 * HK;
   __shared__ float tile[3][SZ][SY][SX];
@@ -240,7 +249,7 @@ constexpr unsigned KNN_PAD_D = 0x7fe00000u;
 template <typename IdxT>
 __global__ void __launch_bounds__(KM_TX* KM_TY* KM_TD, 2)
     knn3d_merge_kernel(const float* __restrict__ xyz, IdxT* __restrict__ idx_out, int D, int H, int W, int dtiles,
-                       unsigned char* __restrict__ cand_out) {
+                       unsigned short* __restrict__ cand_out) {
   __shared__ float4 tile[KM_SZ * KM_SY * KM_SX];  // (x, y, z, 0) incl. the zero-filled 2-wide halo
   __shared__ unsigned short s_dec[128];           // candidate id -> (od + 2) | (oh + 2) << 4 | (ow + 2) << 8
 
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(KM_TX* KM_TY* KM_TD, 2)
     my |= (y + o >= 0 && y + o < H) ? 1u << (o + 2) : 0u;
     mx |= (x + o >= 0 && x + o < W) ? 1u << (o + 2) : 0u;
   }
-  unsigned w4[4] = {0u, 0u, 0u, 0u};
+  unsigned w8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   __align__(16) IdxT vals[16];
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
@@ -348,7 +357,7 @@ __global__ void __launch_bounds__(KM_TX* KM_TY* KM_TD, 2)
     const unsigned f = s_dec[j & 127u];
     const unsigned fd = f & 15u, fh = (f >> 4) & 15u, fw = f >> 8;
     const unsigned in = (mz >> fd) & (my >> fh) & (mx >> fw) & 1u;
-    w4[p >> 2] |= (j | (in ? 0u : 128u)) << (8 * (p & 3));
+    w8[p >> 1] |= knn_code16(fd, fh, fw, j & 127u, in != 0u) << (16 * (p & 1));
     if (idx_out != nullptr) {
       // linear index with the reference's global clamp (torch_utils.py:51-59)
       long long t = n + ((long long)fd - 2) * HW + ((long long)fh - 2) * W + ((long long)fw - 2);
@@ -362,11 +371,15 @@ __global__ void __launch_bounds__(KM_TX* KM_TY* KM_TD, 2)
 #pragma unroll
     for (int p = 0; p < 16; p += VEC) *reinterpret_cast<int4*>(dst + p) = *reinterpret_cast<const int4*>(&vals[p]);
   }
-  if (cand_out != nullptr) *reinterpret_cast<uint4*>(cand_out + point * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+  if (cand_out != nullptr) {
+    uint4* dst = reinterpret_cast<uint4*>(cand_out + point * 16);
+    dst[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+    dst[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+  }
 }
 
 template <int KS, int K>
-static int launch_ks_k(const float* xyz, int64_t* idx64, int32_t* idx32, unsigned char* cand, int clouds, int D, int H,
+static int launch_ks_k(const float* xyz, int64_t* idx64, int32_t* idx32, unsigned short* cand, int clouds, int D, int H,
                        int W, cudaStream_t st) {
   const int dtiles = cdiv(D, KNN_TD);
   dim3 block(KNN_TX, KNN_TY, KNN_TD);
@@ -400,7 +413,7 @@ static int launch_ks(const float* xyz, int64_t* idx64, int32_t* idx32, int cloud
   return PMVS_ERR_ARG;
 }
 
-int launch_knn3d_cand(const float* xyz, int32_t* idx32, unsigned char* cand, int clouds, int D, int H, int W,
+int launch_knn3d_cand(const float* xyz, int32_t* idx32, unsigned short* cand, int clouds, int D, int H, int W,
                       cudaStream_t st) {
   PMVS_REQUIRE(xyz && cand, "knn3d_cand: NULL pointer");
   PMVS_REQUIRE(clouds > 0 && D > 0 && H > 0 && W > 0, "knn3d: empty input");

@@ -303,15 +303,21 @@ class PointFlow(nn.Module):
             nbytes = R * cols * 4
             return ws[o:o + nbytes].view(dtype).view(S, shape.B, N, cols)
 
-        cand = ws[off[8]:off[8] + R * 16].view(S, shape.B, N, 16)
+        cand = ws[off[8]:off[8] + R * 32].view(torch.int16).view(S, shape.B, N, 16)
         if off[9]:
             idx = view(off[2], 16, torch.int32)
         else:
-            # the tile EdgeConv path keeps 1-byte candidate ids only (d*25 + h*5 + w, bit 7 = outside the
-            # grid); the reference's linear index is n + dd*HW + dh*W + dw clamped (torch_utils.py:51-59)
-            j = (cand & 127).to(torch.int64)
+            # the tile EdgeConv path keeps 16-bit neighbour codes only (csrc/knn3d.cu knn_code16): inside the grid
+            # (dd+2)*96 + (dh+2)*12 + (dw+2), outside bit 15 + candidate id d*25 + h*5 + w; the reference's linear
+            # index is n + dd*HW + dh*W + dw clamped (torch_utils.py:51-59)
+            c = cand.to(torch.int64) & 0xFFFF
+            out = (c & 0x8000) != 0
+            j = c & 127
+            dd = torch.where(out, j // 25, c // 96) - 2
+            dh = torch.where(out, (j % 25) // 5, (c % 96) // 12) - 2
+            dw = torch.where(out, j % 5, c % 12) - 2
             n = torch.arange(N, device=ws.device).view(1, 1, N, 1)
-            idx = (n + (j // 25 - 2) * (hs * wsub) + ((j % 25) // 5 - 2) * wsub + (j % 5 - 2)).clamp_(0, N - 1).int()
+            idx = (n + dd * (hs * wsub) + dh * wsub + dw).clamp_(0, N - 1).int()
         return {
             "feature": view(off[0], 136), "xyz": ws[off[1]:off[1] + R * 12].view(torch.float32).view(S, shape.B, 3, N),
             "idx": idx, "cand": cand, "edge": view(off[3], 224), "h2": view(off[4], 16),
