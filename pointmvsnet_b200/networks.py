@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from ._lib import lib, check, stream_ptr, ptr, require_cuda, f32c
+from .nn.conv import Conv2d
 
 _SUPPORTED_COUT = (16, 32, 64, 128)
 
@@ -120,3 +121,55 @@ class EdgeConvNoC(nn.Module):
 
     def forward(self, feature, knn_inds):
         return _edge_layer(self, feature, knn_inds, False)
+
+
+class ImageConv(nn.Module):
+    """The feature-pyramid producer of ``point_flow`` (reference networks.py:84-124, used as ``flow_img_conv`` at
+    model.py:133-148) with the reference's parameter names, so its checkpoints load unchanged - SURVEY.md 8 row f1.
+
+    The convolutions are the stock library's (this module is the boundary before the hot path, not part of it).
+    What changes is the LAYOUT of what it hands over: with ``channels_last=True`` (default) the image is converted
+    once to NHWC, every layer runs in that format, and ``conv1 / conv2 / conv3`` come out as [B,C,h,w] tensors whose
+    memory is [B,h,w,C] - the layout the fetch kernels read.  ``stack_views_channels_last`` then replaces the
+    ``torch.stack(dim=1)`` of model.py:144-145 with a copy into one [B,V,h,w,C] buffer per level (the same bytes the
+    stack moves), and ``PointFlow`` consumes the result zero-copy: the three ``transpose`` launches per pass vanish."""
+
+    def __init__(self, base_channels, channels_last=True):
+        super().__init__()
+        c = base_channels
+        self.base_channels, self.out_channels, self.channels_last = c, 8 * c, bool(channels_last)
+
+        def stage(cin, cout, last_plain=False):
+            tail = nn.Conv2d(cout, cout, 3, padding=1, bias=False) if last_plain else Conv2d(cout, cout, 3, 1, padding=1)
+            return nn.Sequential(Conv2d(cin, cout, 5, stride=2, padding=2), Conv2d(cout, cout, 3, 1, padding=1), tail)
+
+        self.conv0 = nn.Sequential(Conv2d(3, c, 3, 1, padding=1), Conv2d(c, c, 3, 1, padding=1))
+        self.conv1 = stage(c, 2 * c)
+        self.conv2 = stage(2 * c, 4 * c)
+        self.conv3 = stage(4 * c, 8 * c, last_plain=True)
+
+    def forward(self, imgs):
+        x = imgs.contiguous(memory_format=torch.channels_last) if self.channels_last else imgs
+        out = {}
+        for name in ("conv0", "conv1", "conv2", "conv3"):
+            x = getattr(self, name)(x)
+            out[name] = x
+        return out
+
+
+def stack_views_channels_last(per_view, keys=("conv1", "conv2", "conv3"), out=None):
+    """model.py:137-145 (``torch.stack`` of the per-view pyramids along dim 1) for a channels-last producer.
+
+    ``per_view`` is a list (one entry per view) of ``ImageConv`` outputs; returns {key: [B,V,C,h,w]} whose MEMORY is
+    [B,V,h,w,C], i.e. ``t.permute(0,1,3,4,2).is_contiguous()`` - what ``PointFlow.pyramids_to_channels_last`` passes
+    through without a transpose.  ``out`` ({key: [B,V,h,w,C] buffer}) lets a caller reuse the buffers across passes."""
+    V = len(per_view)
+    res = {}
+    for k in keys:
+        first = per_view[0][k]
+        B, C, h, w = first.shape
+        buf = out[k] if out is not None else torch.empty(B, V, h, w, C, device=first.device, dtype=first.dtype)
+        for v, d in enumerate(per_view):
+            buf[:, v].copy_(d[k].permute(0, 2, 3, 1))  # NHWC -> NHWC: a plain contiguous copy for a channels-last source
+        res[k] = buf.permute(0, 1, 4, 2, 3)
+    return res

@@ -675,3 +675,46 @@ def test_point_flow_refuses_eval_mode(golden_weights):
                              torch.zeros(1, 3, 64, 8, 16, device=DEV)],
            cam_params_list=torch.zeros(1, 3, 2, 4, 4, device=DEV), mean=torch.zeros(1, 3, device=DEV),
            std=torch.ones(1, 3, device=DEV))
+
+
+def test_channels_last_image_conv_feeds_point_flow_without_transposes(golden_weights):
+    """``ImageConv(channels_last=True)`` + ``stack_views_channels_last`` hand PointFlow pyramids that
+    already are [B,V,h,w,C] in memory.  They are consumed zero-copy (same storage, three launches fewer than with the
+    reference's NCHW stack) and give the same depth map, bit for bit, as the NCHW copy of the same values."""
+    from pointmvsnet_b200 import _lib
+    from pointmvsnet_b200.networks import ImageConv, stack_views_channels_last
+    from pointmvsnet_b200.synthetic import make_pointflow_inputs
+    H, W, V = 128, 160, 3
+    cpu = make_pointflow_inputs(H, W, V, 1, 48, seed=5)
+    torch.manual_seed(3)
+    conv = ImageConv(8).to(DEV).train()
+    imgs = torch.randn(1, V, 3, H, W, device=DEV)
+    with torch.no_grad():
+        per_view = [conv(imgs[:, v]) for v in range(V)]  # model.py:137-143: one call per view
+        ref_conv = ImageConv(8, channels_last=False).to(DEV).train()
+        ref_conv.load_state_dict(conv.state_dict())
+        nchw_view = ref_conv(imgs[:, 0])
+    for k in ("conv1", "conv2", "conv3"):
+        assert per_view[0][k].is_contiguous(memory_format=torch.channels_last)
+        assert torch.allclose(per_view[0][k], nchw_view[k], atol=1e-4, rtol=1e-4)  # same layer, other cuDNN algorithm
+    pyr_cl = stack_views_channels_last(per_view)
+    levels = [pyr_cl[k] for k in ("conv1", "conv2", "conv3")]
+    pf = _pf(golden_weights)
+    pf.update_running_stats = False
+    passed = pf.pyramids_to_channels_last(levels)
+    for a, b in zip(passed, levels):
+        assert a.data_ptr() == b.data_ptr() and a.is_contiguous()  # no copy, no transpose
+    args = dict(cam_params_list=cpu["cam_params_list"].to(DEV), mean=cpu["mean"].to(DEV), std=cpu["std"].to(DEV),
+                img_hw=cpu["img_hw"])
+    depth, interval = cpu["coarse_depth"].to(DEV), cpu["depth_interval"].to(DEV)
+    with torch.no_grad():
+        pf(depth, interval, 0.125, 0, feature_pyramids=levels, **args)  # workspace + weight upload, not counted
+        torch.cuda.synchronize()
+        n0 = _lib.lib.pmvs_launch_count()
+        d_cl, p_cl = pf(depth, interval, 0.125, 0, feature_pyramids=levels, **args)
+        d_cl, p_cl = d_cl.clone(), p_cl.clone()
+        n1 = _lib.lib.pmvs_launch_count()
+        d_nchw, p_nchw = pf(depth, interval, 0.125, 0, feature_pyramids=[l.contiguous() for l in levels], **args)
+        n2 = _lib.lib.pmvs_launch_count()
+    assert (n2 - n1) - (n1 - n0) == 3, "the NCHW stack costs exactly the three transposes the producer removes"
+    assert torch.equal(d_cl, d_nchw) and torch.equal(p_cl, p_nchw)

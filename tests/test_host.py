@@ -264,3 +264,29 @@ print("DROPIN-OK")
 """ % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "DROPIN-OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_image_conv_producer_names_layout_and_probability_map():
+    """Row f1 on the CPU: ImageConv keeps the reference's parameter names (networks.py:84-111), its channels-last
+    outputs stack into [B,V,h,w,C] memory, and get_propability_map (functions.py:141-175) sums the two bracketing
+    planes."""
+    import torch
+    from pointmvsnet_b200.networks import ImageConv, stack_views_channels_last
+    from pointmvsnet_b200.functions.functions import get_propability_map
+    m = ImageConv(8)
+    keys = list(m.state_dict().keys())
+    assert len(keys) == 61 and keys[0] == "conv0.0.conv.weight" and keys[-1] == "conv3.2.weight"
+    assert "conv1.0.bn.running_mean" in keys and m.out_channels == 64
+    assert m.conv1[0].conv.kernel_size == (5, 5) and m.conv1[0].conv.stride == (2, 2)
+    x = torch.randn(2, 3, 32, 40)
+    per_view = [m(x) for _ in range(3)]
+    stacked = stack_views_channels_last(per_view)
+    for k, c, s in (("conv1", 16, 2), ("conv2", 32, 4), ("conv3", 64, 8)):
+        t = stacked[k]
+        assert tuple(t.shape) == (2, 3, c, 32 // s, 40 // s) and t.permute(0, 1, 3, 4, 2).is_contiguous()
+        assert torch.equal(t[:, 1], per_view[1][k])
+    cv = torch.zeros(1, 4, 1, 3)
+    cv[0, :, 0, :] = torch.tensor([[.1, .2, .3], [.2, .3, .4], [.3, .4, .2], [.4, .1, .1]])
+    depth = torch.tensor([10.5, 12.0, 99.0]).view(1, 1, 1, 3)  # between planes 0/1, exactly plane 2, beyond the last
+    pm = get_propability_map(cv, depth, torch.tensor([10.0]), torch.tensor([1.0]))
+    assert torch.allclose(pm.view(-1), torch.tensor([.1 + .2, .4 + .4, .1 + .1]))
