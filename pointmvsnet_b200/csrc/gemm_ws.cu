@@ -95,20 +95,22 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc {lo, hi}], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major SWIZZLE_128B shared-memory matrix descriptor (see gemm_tc.cu make_desc)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+// one lane of a CONVERGED warp (elect.sync): the issuer of the warp's tcgen05.mma / tcgen05.commit
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -399,9 +401,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
     }
   } else if (warp == MMA_WARP) {
     // =============================== MMA issuer ==========================================================
-    // the whole warp walks the pipeline (converged waits); lane 0 issues the MMAs and commits
+    // The whole warp walks the pipeline CONVERGED and one elected lane issues (elect.sync): in warp-uniform code ptxas
+    // keeps descriptors in uniform registers and emits the UTCHMMAs back to back.  Issued from an `if (lane == 0)`
+    // region every MMA was wrapped in an ELECT / BRA.U.ANY loop with ~10 dependent uniform-datapath instructions -
+    // ~2000 clk of issue latency per 32-channel chunk against 555 clk of tensor-pipe time, which capped every GEMM
+    // of the pass at ~2.7 TB/s (profiles/README_r02.md).
     {
       constexpr uint32_t idesc = make_idesc(128, NT);
+      // K-major SWIZZLE_128B descriptor = {lo: (addr >> 4) | LBO 1, hi: SBO 1024 B | version 1 | swizzle 2};
+      // stage / plane / k-step offsets are plain adds on the low word (the ring lies below 256 KB: no carry)
+      constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t desc_lo0 = (((smem_base + SM_RING) >> 4) & 0x3FFFu) | (1u << 16);
+      constexpr uint32_t D_STAGE = STAGE_BYTES >> 4, D_PLANE = PLANE_BYTES >> 4, D_KSTEP = 32 >> 4;
       int n = 0;
       for (int it = 0; it < tr.count; ++it) {
         const int b = STACKED ? (it & 1) : 0;
@@ -412,22 +423,27 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
         for (int c = 0; c < nch; ++c, ++n) {
           const int stage = n % STAGES;
           mbar_wait(bar_full(stage), (uint32_t)((n / STAGES) & 1));
-          if (lane == 0) {
+          if (elect_one()) {
             fence_proxy_async();  // the producers' generic-proxy stores (acquired above) -> the tensor core's async proxy
             tc_fence_after();
-            const uint32_t x_hi = smem_base + SM_RING + stage * STAGE_BYTES, x_lo = x_hi + PLANE_BYTES;
+            const uint32_t x_hi = desc_lo0 + (uint32_t)stage * D_STAGE, x_lo = x_hi + D_PLANE;
+            const uint32_t a0 = tmem_base + TM_A + (uint32_t)(c * KC);
             const int ksteps = min(KC, K - c * KC) / 8;
-            for (int j = 0; j < ksteps; ++j) {
-              const uint32_t acc = (c == 0 && j == 0) ? 0u : 1u;
-              const uint32_t ka = (uint32_t)(c * KC + j * 8);
+            auto kstep = [&](int j, uint32_t acc) {
               if (STACKED) {
-                umma_tf32_ts(d0, tmem_base + TM_A + ka, make_desc(x_hi + j * 32), idesc, acc);
-                umma_tf32_ts(d0, tmem_base + TM_A + ka, make_desc(x_lo + j * 32), idesc, 1u);
+                umma_tf32_ts(d0, a0 + j * 8, x_hi + j * D_KSTEP, desc_hi, idesc, acc);
+                umma_tf32_ts(d0, a0 + j * 8, x_lo + j * D_KSTEP, desc_hi, idesc, 1u);
               } else {
-                umma_tf32_ts(d0, tmem_base + TM_A + ka, make_desc(x_hi + j * 32), idesc, acc);
-                umma_tf32_ts(d0, tmem_base + TM_A + ka, make_desc(x_lo + j * 32), idesc, 1u);
-                umma_tf32_ts(d0 + NT, tmem_base + TM_A2 + ka, make_desc(x_hi + j * 32), idesc, acc);
+                umma_tf32_ts(d0, a0 + j * 8, x_hi + j * D_KSTEP, desc_hi, idesc, acc);
+                umma_tf32_ts(d0, a0 + j * 8, x_lo + j * D_KSTEP, desc_hi, idesc, 1u);
+                umma_tf32_ts(d0 + NT, a0 + (TM_A2 - TM_A) + j * 8, x_hi + j * D_KSTEP, desc_hi, idesc, acc);
               }
+            };
+            if (ksteps == KC / 8) {
+#pragma unroll
+              for (int j = 0; j < KC / 8; ++j) kstep(j, (c | j) != 0 ? 1u : 0u);
+            } else {
+              for (int j = 0; j < ksteps; ++j) kstep(j, (c | j) != 0 ? 1u : 0u);
             }
             umma_commit(bar_empty(stage));  // the MMAs have consumed this stage's shared memory
             if (c == nch - 1) umma_commit(bar_accf(b));  // accumulator complete
