@@ -42,8 +42,6 @@ constexpr int MMA_WARP = EPI_WARPS;           // warp 4
 constexpr int PROD_WARP0 = EPI_WARPS + 1;     // warps 5..12
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int THREADS = 32 * (EPI_WARPS + 1 + PROD_WARPS);  // 672
-constexpr int XPITCH = 36;                    // floats per accumulator-lane row of the epilogue staging buffer
-constexpr int XBUF_BYTES = 128 * XPITCH * 4;  // 18 432 B: 128 lanes x 32 points (+ pad) of one accumulator slab
 constexpr int MAXK = 224;
 constexpr int A_LD = NT * 8 / PROD_THREADS;   // float4 loads per producer thread and chunk (2)
 
@@ -56,8 +54,7 @@ struct Layout {
   static constexpr int NST = NSTAGES;  // operand stages
   static constexpr int RING = 0;
   static constexpr int STAGING = RING + NST * STAGE_BYTES;
-  static constexpr int XBUF = STAGING + ASYNC * PLANE_BYTES;
-  static constexpr int BN = XBUF + 2 * XBUF_BYTES;
+  static constexpr int BN = STAGING + ASYNC * PLANE_BYTES;
   static constexpr int BAR = BN + 4 * MAXK * 4;
   static constexpr int TOTAL = BAR + 128;
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
@@ -129,6 +126,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 columns, no wait: the caller issues tcgen05.wait::ld after the last load of a batch.  The outputs are written
+// asynchronously, so they must not be read before that wait (volatile asm keeps the order).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
                "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
@@ -161,7 +167,7 @@ template <int COUT, bool IN_BN, int ASYNC, int NSTAGES>
 __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
   using LY = Layout<ASYNC, NSTAGES>;
   constexpr int STAGES = LY::NST;
-  constexpr int SM_RING = LY::RING, SM_STAGING = LY::STAGING, SM_XBUF = LY::XBUF, SM_BN = LY::BN, SM_BAR = LY::BAR;
+  constexpr int SM_RING = LY::RING, SM_STAGING = LY::STAGING, SM_BN = LY::BN, SM_BAR = LY::BAR;
   constexpr int PF = ASYNC > 0 ? ASYNC - 1 : 4;  // chunks of global loads in flight per producer thread
   constexpr bool STACKED = COUT <= 64;
   constexpr int ACC_BUFS = STACKED ? 2 : 1;
@@ -211,8 +217,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
     const int L = warp * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     if (STACKED) {
-      const bool is_hi = L < COUT, is_lo = L >= 64 && L < 64 + COUT;
-      const float* wrow = a.w + (size_t)(is_hi ? L : (is_lo ? L - 64 : 0)) * K;
+      // lane quarter q = 16 channels: lanes [0,16) of the quarter hold W_hi[16q + i], lanes [16,32) W_lo[16q + i],
+      // so the hi and lo products of a channel meet inside ONE epilogue warp (lane ^ 16), no shared-memory exchange
+      const int ch = warp * 16 + (lane & 15);
+      const bool is_hi = lane < 16, live = ch < COUT;
+      const float* wrow = a.w + (size_t)(live ? ch : 0) * K;
       for (int k0 = 0; k0 < K; k0 += 8) {
         float v[8];
         const float4 w0 = ldg4(wrow + k0), w1 = ldg4(wrow + k0 + 4);
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float h = tf32_hi(x[i]);
-          v[i] = is_hi ? h : (is_lo ? __fsub_rn(x[i], h) : 0.f);
+          v[i] = !live ? 0.f : (is_hi ? h : __fsub_rn(x[i], h));
         }
         tmem_st8(lane_addr + TM_A + k0, v);
       }
@@ -456,12 +465,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
     // =============================== epilogue ===========================================================
     const int q = warp;  // TMEM lane quarter
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t xs = smem_base + SM_XBUF;  // 2 x [128 lanes][XPITCH] floats
-    // stacked: accumulator lanes [0,64) = W_hi * X, [64,128) = W_lo * X of channels [0,64).  A slab (32 points) of
-    // all 128 lanes goes through shared memory; afterwards warp q adds the halves of points [8q, 8q+8) for the
-    // channels `lane` and `lane + 32` and stores them (32 consecutive channels of a point = one 128-byte line).
-    constexpr int NCH_T = STACKED ? 2 : 1;   // channels per thread
-    const int chs[2] = {STACKED ? lane : q * 32 + lane, lane + 32};
+    // stacked: lane 32q + i of the accumulator = W_hi * X (i < 16) or W_lo * X (i >= 16) of channel 16q + (i & 15),
+    // column = point.  hi + lo is one shuffle with lane ^ 16; the lower half-warp then owns the even points of the
+    // slab and the upper half the odd ones: a store instruction writes 16 consecutive channels of two points.
+    constexpr int NCH_T = 1;   // channels per thread
+    const int half = lane >> 4;
+    const int chs[1] = {STACKED ? q * 16 + (lane & 15) : q * 32 + lane};
     double acc1[NCH_T], acc2[NCH_T];
 #pragma unroll
     for (int h = 0; h < NCH_T; ++h) acc1[h] = acc2[h] = 0.0;
@@ -497,72 +506,48 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
       float s1[NCH_T], s2[NCH_T];
 #pragma unroll
       for (int h = 0; h < NCH_T; ++h) s1[h] = s2[h] = 0.f;
+      if (STACKED) {
 #pragma unroll 1
-      for (int slab = 0; slab < NT / 32; ++slab) {
-        float v[32];
-        tmem_ld32(d0 + slab * 32, v);
-        if (STACKED) {
-          const uint32_t xb = xs + (slab & 1) * XBUF_BYTES;
-          const uint32_t xrow = xb + (q * 32 + lane) * (XPITCH * 4);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) sts128(xrow + j * 4, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          named_bar_sync(2 + (slab & 1), EPI_WARPS * 32);
-          const int p0 = slab * 32 + q * 8;  // first of this warp's 8 points of the slab
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int ch = chs[h];
-            const uint32_t hi = xb + (ch * XPITCH + q * 8) * 4;
-            const uint32_t lo = hi + 64 * XPITCH * 4;
-            const float4 h0 = lds128(hi), h1 = lds128(hi + 16);
-            const float4 l0 = lds128(lo), l1 = lds128(lo + 16);
-            const float o[8] = {h0.x + l0.x, h0.y + l0.y, h0.z + l0.z, h0.w + l0.w,
-                                h1.x + l1.x, h1.y + l1.y, h1.z + l1.z, h1.w + l1.w};
-            if (ch < COUT) {
-              float* yp = a.y + (grow0 + p0) * a.ldy + ch;
-              if (p0 + 8 <= rows_valid) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  *yp = o[i];
-                  yp += a.ldy;
-                  s1[h] += o[i];
-                  s2[h] = fmaf(o[i], o[i], s2[h]);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  if (p0 + i < rows_valid) {
-                    yp[(size_t)i * a.ldy] = o[i];
-                    s1[h] += o[i];
-                    s2[h] = fmaf(o[i], o[i], s2[h]);
-                  }
-                }
-              }
-            }
-          }
-        } else {
-          float v2[32];
-          tmem_ld32(d0 + NT + slab * 32, v2);
+        for (int slab = 0; slab < NT / 32; ++slab) {
+          float v[32];
+          tmem_ld32(d0 + slab * 32, v);
           const int ch = chs[0];
-          float* yp = a.y + (grow0 + slab * 32) * a.ldy + ch;
-          if (slab * 32 + 32 <= rows_valid) {
+          float* yp = a.y + (grow0 + slab * 32 + half) * a.ldy + ch;
+          const int pmax = rows_valid - slab * 32 - half;  // this half-warp's point 2*jj + half is valid iff 2*jj < pmax
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float o = v[j] + v2[j];
+          for (int jj = 0; jj < 16; ++jj) {
+            // lower half keeps its even point and hands over its odd one; the upper half the other way round
+            const float mine = half ? v[2 * jj + 1] : v[2 * jj];
+            const float send = half ? v[2 * jj] : v[2 * jj + 1];
+            const float o = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+            if (ch < COUT && 2 * jj < pmax) {
               *yp = o;
-              yp += a.ldy;
               s1[0] += o;
               s2[0] = fmaf(o, o, s2[0]);
             }
-          } else {
+            yp += 2 * a.ldy;
+          }
+        }
+      } else {
+        // lane = channel in both accumulators (W_hi * X and W_lo * X_hi): plain add, 16 points at a time
+#pragma unroll 1
+        for (int hs = 0; hs < NT / 16; ++hs) {
+          float v[16], v2[16];
+          tmem_ld16_nowait(d0 + hs * 16, v);
+          tmem_ld16_nowait(d0 + NT + hs * 16, v2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int ch = chs[0];
+          float* yp = a.y + (grow0 + hs * 16) * a.ldy + ch;
+          const int pmax = rows_valid - hs * 16;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (slab * 32 + j < rows_valid) {
-                const float o = v[j] + v2[j];
-                yp[(size_t)j * a.ldy] = o;
-                s1[0] += o;
-                s2[0] = fmaf(o, o, s2[0]);
-              }
+          for (int j = 0; j < 16; ++j) {
+            const float o = v[j] + v2[j];
+            if (j < pmax) {
+              *yp = o;
+              s1[0] += o;
+              s2[0] = fmaf(o, o, s2[0]);
             }
+            yp += a.ldy;
           }
         }
       }
@@ -609,6 +594,7 @@ static int launch_one(const GemmArgs& a, cudaStream_t st, const char* name) {
   // the kernels sit at ~70 % of what a read-dominated stream reaches on this part (profiles/r02/hbm_read_probe.txt),
   // not at a pipeline-depth limit.  Two are kept: the default and the register-prefetch form.
   if (opt(OPT_GEMM) == 1) return launch_pf<COUT, IN_BN, 0, 4>(a, st, name);  // register prefetch, 4 chunks in flight, 4 operand stages
+  if (opt(OPT_GEMM) == 3) return launch_pf<COUT, IN_BN, 5, 4>(a, st, name);  // as below with 4 operand stages (212 KB)
   return launch_pf<COUT, IN_BN, 5, 3>(a, st, name);  // cp.async staging: 4 chunks (64 KB) in flight, 3 operand stages
 }
 
