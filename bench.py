@@ -758,8 +758,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--views-in-flight", type=int, default=2,
-                    help="independent reference views whose passes run concurrently on one GPU (default 2)")
+    ap.add_argument("--views-in-flight", type=int, default=4,
+                    help="independent reference views whose passes run concurrently on one GPU (default 4: measured "
+                         "1 -> 2 -> 4 views = 1.00 / 1.11 / 1.17x the single-view rate at C2)")
     ap.add_argument("--mode", default="fused", choices=["fused", "oplevel"],
                     help="fused: the PointFlow module (default); oplevel: the reference closure over the stand-alone "
                          "operators (what an unchanged model.py runs)")

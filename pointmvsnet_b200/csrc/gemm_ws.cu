@@ -135,6 +135,14 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16])
         "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
       : "r"(taddr));
 }
+// tcgen05.wait::ld with the loaded registers as in/out operands: their uses cannot be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld16(float (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                 "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
                "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
@@ -170,7 +178,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
   constexpr int SM_RING = LY::RING, SM_STAGING = LY::STAGING, SM_BN = LY::BN, SM_BAR = LY::BAR;
   constexpr int PF = ASYNC > 0 ? ASYNC - 1 : 4;  // chunks of global loads in flight per producer thread
   constexpr bool STACKED = COUT <= 64;
-  constexpr int ACC_BUFS = STACKED ? 2 : 1;
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B operands need 1024-byte alignment
   const uint32_t smem_base = smem_u32(smem);
   float* sBN = (float*)(smem + SM_BN);  // mean, istd, gamma, beta x MAXK
@@ -361,10 +368,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
           // rows / columns beyond the valid range were loaded as zeros and must stay zero
           const int r = prow + ROWS_STEP * i;
           if (k0 < K && r < a.rows_per_group - cp.row0) {
-            v.x = fmaxf(bn_apply(v.x, sBN[k0 + 0], sBN[MAXK + k0 + 0], sBN[2 * MAXK + k0 + 0], sBN[3 * MAXK + k0 + 0]), 0.f);
-            v.y = fmaxf(bn_apply(v.y, sBN[k0 + 1], sBN[MAXK + k0 + 1], sBN[2 * MAXK + k0 + 1], sBN[3 * MAXK + k0 + 1]), 0.f);
-            v.z = fmaxf(bn_apply(v.z, sBN[k0 + 2], sBN[MAXK + k0 + 2], sBN[2 * MAXK + k0 + 2], sBN[3 * MAXK + k0 + 2]), 0.f);
-            v.w = fmaxf(bn_apply(v.w, sBN[k0 + 3], sBN[MAXK + k0 + 3], sBN[2 * MAXK + k0 + 3], sBN[3 * MAXK + k0 + 3]), 0.f);
+            // k0 is a multiple of 4 and the four tables start MAXK floats apart: four 128-bit loads
+            const float4 m = *reinterpret_cast<const float4*>(&sBN[k0]);
+            const float4 is = *reinterpret_cast<const float4*>(&sBN[MAXK + k0]);
+            const float4 gm = *reinterpret_cast<const float4*>(&sBN[2 * MAXK + k0]);
+            const float4 bt = *reinterpret_cast<const float4*>(&sBN[3 * MAXK + k0]);
+            v.x = fmaxf(bn_apply(v.x, m.x, is.x, gm.x, bt.x), 0.f);
+            v.y = fmaxf(bn_apply(v.y, m.y, is.y, gm.y, bt.y), 0.f);
+            v.z = fmaxf(bn_apply(v.z, m.z, is.z, gm.z, bt.z), 0.f);
+            v.w = fmaxf(bn_apply(v.w, m.w, is.w, gm.w, bt.w), 0.f);
           }
         }
         float4 hi, lo;
@@ -424,11 +436,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
       constexpr uint32_t D_STAGE = STAGE_BYTES >> 4, D_PLANE = PLANE_BYTES >> 4, D_KSTEP = 32 >> 4;
       int n = 0;
       for (int it = 0; it < tr.count; ++it) {
-        const int b = STACKED ? (it & 1) : 0;
-        const int use = STACKED ? (it >> 1) : it;
+        const int b = it & 1, use = it >> 1;
         mbar_wait(bar_acce(b), (uint32_t)((use & 1) ^ 1));  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d0 = tmem_base + TM_D + (STACKED ? b * NT : 0);
+        const uint32_t d0 = tmem_base + TM_D + b * NT;
         for (int c = 0; c < nch; ++c, ++n) {
           const int stage = n % STAGES;
           mbar_wait(bar_full(stage), (uint32_t)((n / STAGES) & 1));
@@ -445,7 +456,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
               } else {
                 umma_tf32_ts(d0, a0 + j * 8, x_hi + j * D_KSTEP, desc_hi, idesc, acc);
                 umma_tf32_ts(d0, a0 + j * 8, x_lo + j * D_KSTEP, desc_hi, idesc, 1u);
-                umma_tf32_ts(d0 + NT, a0 + (TM_A2 - TM_A) + j * 8, x_hi + j * D_KSTEP, desc_hi, idesc, acc);
+                umma_tf32_ts(d0, a0 + (TM_A2 - TM_A) + j * 8, x_hi + j * D_KSTEP, desc_hi, idesc, 1u);  // W_lo * X_hi
               }
             };
             if (ksteps == KC / 8) {
@@ -498,15 +509,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
         flush();
         acc_g = g;
       }
-      const int b = STACKED ? (it & 1) : 0;
-      const int use = STACKED ? (it >> 1) : it;
+      const int b = it & 1, use = it >> 1;
       mbar_wait(bar_accf(b), (uint32_t)(use & 1));
       tc_fence_after();
-      const uint32_t d0 = lane_addr + TM_D + (STACKED ? b * NT : 0);
+      const uint32_t d0 = lane_addr + TM_D + b * NT;
       float s1[NCH_T], s2[NCH_T];
 #pragma unroll
       for (int h = 0; h < NCH_T; ++h) s1[h] = s2[h] = 0.f;
       if (STACKED) {
+        // 32 points per step.  (Measured: 16-column steps with the next tcgen05.ld in flight during the stores were
+        // 6-12 % SLOWER for the stacked shapes - twice the TMEM loads and waits for the same data.)
 #pragma unroll 1
         for (int slab = 0; slab < NT / 32; ++slab) {
           float v[32];
@@ -529,26 +541,32 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
           }
         }
       } else {
-        // lane = channel in both accumulators (W_hi * X and W_lo * X_hi): plain add, 16 points at a time
-#pragma unroll 1
-        for (int hs = 0; hs < NT / 16; ++hs) {
-          float v[16], v2[16];
-          tmem_ld16_nowait(d0 + hs * 16, v);
-          tmem_ld16_nowait(d0 + NT + hs * 16, v2);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int ch = chs[0];
-          float* yp = a.y + (grow0 + hs * 16) * a.ldy + ch;
-          const int pmax = rows_valid - hs * 16;
+        // lane = channel; W_hi * (X_hi + X_lo) + W_lo * X_hi were accumulated in place.  16 points at a time, the
+        // tcgen05.ld of the next 16 columns in flight while the current ones are stored
+        auto consume = [&](const float (&v)[16], int p0) {
+          float* yp = a.y + (grow0 + p0) * a.ldy + chs[0];
+          const int pmax = rows_valid - p0;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float o = v[j] + v2[j];
             if (j < pmax) {
-              *yp = o;
-              s1[0] += o;
-              s2[0] = fmaf(o, o, s2[0]);
+              *yp = v[j];
+              s1[0] += v[j];
+              s2[0] = fmaf(v[j], v[j], s2[0]);
             }
             yp += a.ldy;
           }
+        };
+        float va[16], vb[16];
+        tmem_ld16_nowait(d0, va);
+        tmem_wait_ld16(va);
+#pragma unroll 1
+        for (int hs = 0; hs < NT / 16; hs += 2) {
+          tmem_ld16_nowait(d0 + (hs + 1) * 16, vb);
+          consume(va, hs * 16);
+          tmem_wait_ld16(vb);
+          if (hs + 2 < NT / 16) tmem_ld16_nowait(d0 + (hs + 2) * 16, va);
+          consume(vb, (hs + 1) * 16);
+          if (hs + 2 < NT / 16) tmem_wait_ld16(va);
         }
       }
       tc_fence_before();
@@ -594,7 +612,6 @@ static int launch_one(const GemmArgs& a, cudaStream_t st, const char* name) {
   // the kernels sit at ~70 % of what a read-dominated stream reaches on this part (profiles/r02/hbm_read_probe.txt),
   // not at a pipeline-depth limit.  Two are kept: the default and the register-prefetch form.
   if (opt(OPT_GEMM) == 1) return launch_pf<COUT, IN_BN, 0, 4>(a, st, name);  // register prefetch, 4 chunks in flight, 4 operand stages
-  if (opt(OPT_GEMM) == 3) return launch_pf<COUT, IN_BN, 5, 4>(a, st, name);  // as below with 4 operand stages (212 KB)
   return launch_pf<COUT, IN_BN, 5, 3>(a, st, name);  // cp.async staging: 4 chunks (64 KB) in flight, 3 operand stages
 }
 
