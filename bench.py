@@ -524,7 +524,7 @@ def run_ours(args):
         achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(achieved / hbm_peak, 4), "traffic": traffic.get(dom),
-                    "traffic_source": ("static: ncu --set full capture, profiles/dram_traffic.json (%s)" %
+                    "traffic_source": ("static: ncu capture of one pass, profiles/dram_traffic.json (%s)" %
                                        traffic.get("_capture", "see its _comment")) if traffic.get(dom) else None,
                     "numerator": "bytes this kernel must read + write once given its boundaries (DESIGN.md 3); the "
                                  "SURVEY 8(d) stage figures are in roofline_stage",
