@@ -89,6 +89,15 @@ int pmvs_gather_knn_forward(const float* input, const int64_t* index, float* out
 /* grad_in[b,c,idx[b,n,k]] += grad_out[b,c,n,k]; grad_in [B,C,N] is zeroed inside. */
 int pmvs_gather_knn_backward(const float* grad_output, const int64_t* index, float* grad_input,
                              int B, int C, int N, int K, pmvs_stream_t stream);
+/* The same sums with a FIXED summation order: grad_in[b,c,j] adds its contributions
+ * sequentially in ascending source position n*K + k, so the result is bit-reproducible (the reference's atomicAdd
+ * scatter, gather_knn_kernel.cu:50-89, is not) and equals the CPU loop `for p: grad_in[idx[p]] += grad_out[p]`.
+ * Any index tensor; out-of-range entries are skipped.  workspace: pmvs_gather_knn_backward_det_workspace_bytes(B, N, K)
+ * bytes, 256-byte aligned, device memory. */
+size_t pmvs_gather_knn_backward_det_workspace_bytes(int B, int N, int K);
+int pmvs_gather_knn_backward_det(const float* grad_output, const int64_t* index, float* grad_input,
+                                 int B, int C, int N, int K, void* workspace, size_t workspace_bytes,
+                                 pmvs_stream_t stream);
 
 /* ---- a10: get_knn_3d  (utils/torch_utils.py:16-61) ------------------------------- */
 /* xyz [B,3,D,H,W] -> idx [B, D*H*W, knn]; exactly one of idx64 / idx32 may be NULL.

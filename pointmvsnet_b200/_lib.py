@@ -62,6 +62,8 @@ _sig("pmvs_profile_enable", I, [I])
 _sig("pmvs_profile_collect", I, [C.c_char_p, C.c_size_t, P, I])
 _sig("pmvs_gather_knn_forward", I, [P, P, P, I, I, I, I, P])
 _sig("pmvs_gather_knn_backward", I, [P, P, P, I, I, I, I, P])
+_sig("pmvs_gather_knn_backward_det_workspace_bytes", C.c_size_t, [I, I, I])
+_sig("pmvs_gather_knn_backward_det", I, [P, P, P, I, I, I, I, P, C.c_size_t, P])
 _sig("pmvs_knn3d", I, [P, P, P, I, I, I, I, I, I, P])
 _sig("pmvs_feature_fetch", I, [P, P, P, P, P, I, I, I, I, I, I, P])
 _sig("pmvs_feature_fetch_backward", I, [P, P, P, P, P, I, I, I, I, I, I, P])
@@ -78,7 +80,7 @@ _sig("pmvs_point_flow_debug_offsets", I, [C.POINTER(FlowShape), C.POINTER(C.c_si
 
 EXPORTED = [
     "pmvs_version", "pmvs_last_error", "pmvs_launch_count", "pmvs_set_option", "pmvs_get_option", "pmvs_profile_enable", "pmvs_profile_collect", "pmvs_set_gemm_mode", "pmvs_get_gemm_mode", "pmvs_gather_knn_forward",
-    "pmvs_gather_knn_backward", "pmvs_knn3d", "pmvs_feature_fetch", "pmvs_feature_fetch_backward",
+    "pmvs_gather_knn_backward", "pmvs_gather_knn_backward_det_workspace_bytes", "pmvs_gather_knn_backward_det", "pmvs_knn3d", "pmvs_feature_fetch", "pmvs_feature_fetch_backward",
     "pmvs_cost_volume", "pmvs_transpose", "pmvs_idx64_to_idx32", "pmvs_edgeconv_pm", "pmvs_linear_pm", "pmvs_point_flow_workspace_bytes",
     "pmvs_point_flow_iter", "pmvs_pyramid_to_channels_last", "pmvs_point_flow_debug_offsets",
 ]

@@ -37,8 +37,12 @@ def gather_knn_forward(input, index):
     return out
 
 
-def gather_knn_backward(grad_output, index):
-    """grad_output [B,C,N,K], index [B,N,K] -> grad_input [B,C,N] (scatter-add)."""
+def gather_knn_backward(grad_output, index, deterministic=True):
+    """grad_output [B,C,N,K], index [B,N,K] -> grad_input [B,C,N] (scatter-add).
+
+    ``deterministic=True`` (default): segmented reduction with a fixed summation order
+    (``pmvs_gather_knn_backward_det``) - bit-reproducible, unlike the reference's ``atomicAdd`` scatter
+    (gather_knn_kernel.cu:50-89).  ``False`` selects the atomic scatter (same sums up to fp32 rounding order)."""
     _check_inputs("grad_output", grad_output, 4, index)
     if index.size(2) != grad_output.size(3):
         raise RuntimeError("index.size(2) does not equal to k")
@@ -47,5 +51,13 @@ def gather_knn_backward(grad_output, index):
     B, Cc, N, K = g.shape
     out = torch.empty(B, Cc, N, device=g.device, dtype=torch.float32)
     with torch.cuda.device(g.device):
-        check(lib.pmvs_gather_knn_backward(ptr(g), ptr(ind), ptr(out), B, Cc, N, K, stream_ptr()))
+        if deterministic:
+            nbytes = lib.pmvs_gather_knn_backward_det_workspace_bytes(B, N, K)
+            ws = torch.empty(nbytes + 256, device=g.device, dtype=torch.uint8)
+            base = ws.data_ptr()
+            aligned = (base + 255) & ~255
+            check(lib.pmvs_gather_knn_backward_det(ptr(g), ptr(ind), ptr(out), B, Cc, N, K, aligned,
+                                                   nbytes + 256 - (aligned - base), stream_ptr()))
+        else:
+            check(lib.pmvs_gather_knn_backward(ptr(g), ptr(ind), ptr(out), B, Cc, N, K, stream_ptr()))
     return out

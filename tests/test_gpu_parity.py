@@ -724,3 +724,59 @@ def test_channels_last_image_conv_feeds_point_flow_without_transposes(golden_wei
         n2 = _lib.lib.pmvs_launch_count()
     assert (n2 - n1) - (n1 - n0) == 3, "the NCHW stack costs exactly the three transposes the producer removes"
     assert torch.equal(d_cl, d_nchw) and torch.equal(p_cl, p_nchw)
+
+
+def _scatter_reference(gout, idx, N):
+    """`for p in range(N*K): grad_in[idx[p]] += grad_out[p]`, fp32, in that order (numpy, per batch and channel)."""
+    B, C, _, K = gout.shape
+    res = np.zeros((B, C, N), dtype=np.float32)
+    g = gout.reshape(B, C, -1)
+    flat = idx.reshape(B, -1)
+    for b in range(B):
+        order = np.argsort(flat[b], kind="stable")  # ascending destination, ascending source position inside
+        dest = flat[b][order]
+        for c in range(C):
+            vals = g[b, c][order]
+            acc = np.float32(0)
+            prev = -1
+            for d, v in zip(dest, vals):
+                if d < 0 or d >= N:
+                    continue
+                if d != prev:
+                    if prev >= 0:
+                        res[b, c, prev] = acc
+                    acc, prev = np.float32(0), d
+                acc = np.float32(acc + v)
+            if prev >= 0:
+                res[b, c, prev] = acc
+    return res
+
+
+@pytest.mark.parametrize("case", ["knn_window", "random", "hot_row"])
+def test_gather_knn_backward_deterministic_segmented_reduce(case):
+    """the deterministic GatherKNNBackward.  Bit-identical to the sequential CPU scatter in source
+    order, identical between runs, and equal to the atomic scatter up to fp32 summation order - for the structured
+    lists of get_knn_3d, for arbitrary indices (with out-of-range entries, which are skipped) and for a row that
+    collects thousands of contributions (the long-segment path)."""
+    from pointmvsnet_b200.functions import dgcnn_ext
+    from pointmvsnet_b200.utils.torch_utils import get_knn_3d
+    torch.manual_seed(11)
+    if case == "knn_window":
+        xyz = torch.randn(2, 3, 5, 12, 20, device=DEV)
+        idx = get_knn_3d(xyz, 5, knn=16)
+        B, N, K, C = 2, 5 * 12 * 20, 16, 5
+    elif case == "random":
+        B, N, K, C = 2, 333, 7, 4
+        idx = torch.randint(-2, N + 2, (B, N, K), device=DEV)
+    else:
+        B, N, K, C = 1, 700, 8, 3
+        idx = torch.randint(0, N, (B, N, K), device=DEV)
+        idx[:, :, :6] = 17  # 4 200 contributions to one row
+    gout = torch.randn(B, C, N, K, device=DEV) * 3
+    a = dgcnn_ext.gather_knn_backward(gout, idx)
+    b = dgcnn_ext.gather_knn_backward(gout, idx)
+    atomic = dgcnn_ext.gather_knn_backward(gout, idx, deterministic=False)
+    assert torch.equal(a, b)
+    ref = _scatter_reference(gout.cpu().numpy(), idx.cpu().numpy(), N)
+    assert np.array_equal(a.cpu().numpy(), ref)
+    assert torch.allclose(a, atomic, rtol=1e-5, atol=1e-3 if case == "hot_row" else 1e-4)
