@@ -306,318 +306,8 @@ __global__ void __launch_bounds__(ET_THREADS, 3) edge_tile_kernel(const __grid_c
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Ring variant (PMVS_OPT_EDGE = 2): ONE persistent CTA per SM, a 3-deep ring of halo boxes filled by a producer
-// warp's TMA loads two items ahead, 20 consumer warps working on the same box (2 steps of 80 points).  The one-tile
-// kernel above spends 23 % of its warp samples waiting for its own TMA load (ncu source page, profiles/README_r02.md):
-// three co-resident CTAs do not cover a 61 KB load each.  Work = contiguous ranges of (group, tile) with both
-// 32-channel slabs of a tile back to back; BatchNorm groups change at most a few times per CTA.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int ER_CONS_WARPS = 20;                      // 20 warps x 4 points = 80 points per step, 2 steps per box
-constexpr int ER_CONS_THREADS = ER_CONS_WARPS * 32;    // 640
-constexpr int ER_THREADS = ER_CONS_THREADS + 32;       // + the TMA producer warp
-constexpr int ER_NBUF = 3;
-
-__device__ __forceinline__ void er_wait(unsigned bar, unsigned parity) {
-  unsigned done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void er_cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ER_CONS_THREADS) : "memory"); }
-
-template <int COUT, bool APPLY>
-__global__ void __launch_bounds__(ER_THREADS, 1) edge_ring_kernel(const __grid_constant__ CUtensorMap tm,
-                                                                   const EdgeTileArgs a) {
-  using G = TileGeom<8, 4>;
-  constexpr int TX = 8, TY = 4;
-  constexpr int LD = 2 * COUT;
-  constexpr int SLABS = COUT / ET_CP;
-  constexpr int STEPS = G::NPTS / (ER_CONS_WARPS * ET_PPW);  // 2
-  static_assert(G::NPTS == STEPS * ER_CONS_WARPS * ET_PPW, "edge_ring: 160 points = 2 steps of 80");
-  constexpr int LAYER = G::HY * G::HX * ET_CP;
-  extern __shared__ __align__(128) float ring[];  // ER_NBUF x [ROWS][32]
-  __shared__ __align__(8) unsigned long long bars[2 * ER_NBUF];
-  __shared__ float part[APPLY ? 1 : ER_CONS_WARPS][APPLY ? 1 : 2 * ET_CP];
-  __shared__ __align__(16) float coef[APPLY ? ET_COEF * COUT : 4];
-  __shared__ int s_last;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int gh = a.gh, gw = a.gw;
-  const int tiles_x = (gw + TX - 1) / TX, tiles_per_cloud = tiles_x * ((gh + TY - 1) / TY);
-  const int tiles_per_group = tiles_per_cloud * a.clouds_per_group;
-  const int HW = gh * gw, N = PMVS_NUM_HYP * HW;
-  const int rows_per_group = a.clouds_per_group * N;
-  const long long total_tiles = (long long)a.groups * tiles_per_group;
-  const long long t_lo = blockIdx.x * total_tiles / gridDim.x, t_hi = (blockIdx.x + 1ll) * total_tiles / gridDim.x;
-  const unsigned bar0 = smem_u32(bars);
-  auto bar_full = [&](int b) { return bar0 + 8u * (unsigned)b; };
-  auto bar_empty = [&](int b) { return bar0 + 8u * (unsigned)(ER_NBUF + b); };
-
-  if (tid == 0) {
-    for (int b = 0; b < ER_NBUF; ++b) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_full(b)));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_empty(b)), "n"(ER_CONS_WARPS));
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == ER_CONS_WARPS) {
-    // ================================ producer: TMA loads, up to ER_NBUF boxes ahead ================================
-    unsigned n = 0;
-    for (long long t = t_lo; t < t_hi; ++t) {
-      const int g = (int)(t / tiles_per_group), tile = (int)(t - (long long)g * tiles_per_group);
-      const int b = tile / tiles_per_cloud, tr = tile - b * tiles_per_cloud;
-      const int y0 = (tr / tiles_x) * TY, x0 = (tr % tiles_x) * TX;
-#pragma unroll 1
-      for (int slab = 0; slab < SLABS; ++slab, ++n) {
-        const unsigned buf = n % ER_NBUF;
-        er_wait(bar_empty(buf), ((n / ER_NBUF) & 1u) ^ 1u);
-        if (lane == 0) {
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full(buf)),
-                       "r"((unsigned)G::BYTES)
-                       : "memory");
-          asm volatile(
-              "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-              ::"r"(smem_u32(ring) + buf * (unsigned)G::BYTES), "l"(&tm), "r"(COUT + slab * ET_CP), "r"(x0 - 2),
-              "r"(y0 - 2), "r"((g * a.clouds_per_group + b) * PMVS_NUM_HYP), "r"(bar_full(buf))
-              : "memory");
-        }
-        __syncwarp();
-      }
-    }
-    return;
-  }
-
-  // ==================================== consumers ===================================================================
-  const int sub = lane / ET_LPP, cl = (lane % ET_LPP) * 4;
-  // point q = step * 80 + warp * 4 + sub of the box: x = q % 8, y = (q / 8) % 4, layer = q / 32
-  int ptx[STEPS], pty[STEPS], pd[STEPS], pb0[STEPS];
-#pragma unroll
-  for (int s = 0; s < STEPS; ++s) {
-    const int q = s * (ER_CONS_WARPS * ET_PPW) + warp * ET_PPW + sub;
-    ptx[s] = q % TX; pty[s] = (q / TX) % TY; pd[s] = q / (TX * TY);
-    pb0[s] = (((pd[s] - 2) * G::HY + pty[s]) * G::HX + ptx[s]) * ET_CP + cl;
-  }
-  f32x2 acc[SLABS][4];
-#pragma unroll
-  for (int sl = 0; sl < SLABS; ++sl)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[sl][q] = pack2(0.f, 0.f);
-  int cur_g = -1, tiles_in_g = 0;
-
-  // statistics of the group just finished: warp shuffles -> shared memory -> fp64 atomics -> ticket (in tiles);
-  // the CTA that completes the group's tile count turns the sums into the coefficient table
-  auto flush_group = [&]() {
-    if (APPLY || cur_g < 0) return;
-#pragma unroll
-    for (int sl = 0; sl < SLABS; ++sl) {
-      float v[8];
-      unpack2(acc[sl][0], v[0], v[1]); unpack2(acc[sl][1], v[2], v[3]);
-      unpack2(acc[sl][2], v[4], v[5]); unpack2(acc[sl][3], v[6], v[7]);
-#pragma unroll
-      for (int off = ET_LPP; off < 32; off <<= 1) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
-      }
-      er_cons_sync();  // the previous slab's readers of `part` are done
-      if (sub == 0) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) part[warp][(q >> 2) * ET_CP + cl + (q & 3)] = v[q];
-      }
-      er_cons_sync();
-      if (tid < 2 * ET_CP) {
-        double t = 0.0;
-#pragma unroll
-        for (int wq = 0; wq < ER_CONS_WARPS; ++wq) t += (double)part[wq][tid];
-        atomicAdd(a.nstats + (size_t)cur_g * 2 * COUT + (tid / ET_CP) * COUT + sl * ET_CP + (tid % ET_CP), t);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[sl][q] = pack2(0.f, 0.f);
-    }
-    __threadfence();
-    er_cons_sync();
-    if (tid == 0) {
-      const unsigned old = atomicAdd(a.ticket + cur_g, (unsigned)tiles_in_g);
-      s_last = old + (unsigned)tiles_in_g == (unsigned)tiles_per_group;
-    }
-    er_cons_sync();
-    if (s_last) {
-      __threadfence();
-      const double* sc = a.cstats + (size_t)cur_g * 4 * COUT;
-      const double* sn = a.nstats + (size_t)cur_g * 2 * COUT;
-      float* cg = a.coef + (size_t)cur_g * ET_COEF * COUT;
-      const double cnt_c = (double)rows_per_group, cnt_n = (double)rows_per_group * PMVS_KNN;
-      for (int c = tid; c < COUT; c += ER_CONS_THREADS) {
-        const BnCoef kn = bn_coef(__ldcg(sn + c), __ldcg(sn + COUT + c), cnt_n, a.eps);
-        const int gn = a.concat_central ? COUT + c : c;
-        const float A = kn.invstd * a.gamma[gn];
-        cg[c] = A;
-        cg[COUT + c] = fmaf(-kn.mean, A, a.beta[gn]);
-        if (a.concat_central) {
-          const BnCoef kc = bn_coef(sc[c], sc[2 * COUT + c], cnt_c, a.eps);
-          cg[2 * COUT + c] = kc.mean; cg[3 * COUT + c] = kc.invstd; cg[4 * COUT + c] = a.gamma[c]; cg[5 * COUT + c] = a.beta[c];
-        }
-      }
-    }
-  };
-
-  unsigned n = 0;
-#pragma unroll 1
-  for (long long t = t_lo; t < t_hi; ++t) {
-    const int g = (int)(t / tiles_per_group), tile = (int)(t - (long long)g * tiles_per_group);
-    if (g != cur_g) {  // uniform over the consumers
-      flush_group();
-      cur_g = g;
-      tiles_in_g = 0;
-      if (APPLY) {
-        er_cons_sync();  // nobody reads the previous group's coefficients any more
-        const float* cgp = a.coef + (size_t)g * ET_COEF * COUT;
-        for (int c = tid; c < ET_COEF * COUT; c += ER_CONS_THREADS) coef[c] = __ldg(cgp + c);
-        er_cons_sync();
-      }
-    }
-    ++tiles_in_g;
-    const int b = tile / tiles_per_cloud, tr = tile - b * tiles_per_cloud;
-    const int y0 = (tr / tiles_x) * TY, x0 = (tr % tiles_x) * TX;
-    const size_t cloud_base = (size_t)g * rows_per_group + (size_t)b * N;
-    bool ok[STEPS];
-    int pn[STEPS];
-    uint4 c0[STEPS], c1[STEPS];
-#pragma unroll
-    for (int s = 0; s < STEPS; ++s) {
-      ok[s] = y0 + pty[s] < gh && x0 + ptx[s] < gw;
-      pn[s] = pd[s] * HW + (y0 + pty[s]) * gw + x0 + ptx[s];
-      if (ok[s]) {  // the 16 x 16-bit neighbour codes (shared by the slabs of the tile)
-        const uint4* cp = reinterpret_cast<const uint4*>(a.cand + (cloud_base + (size_t)pn[s]) * PMVS_KNN);
-        c0[s] = __ldg(cp);
-        c1[s] = __ldg(cp + 1);
-      } else {
-        c0[s] = c1[s] = make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-#pragma unroll
-    for (int slab = 0; slab < SLABS; ++slab, ++n) {
-      const int ch0 = slab * ET_CP;
-      float4 loc[STEPS];
-#pragma unroll
-      for (int s = 0; s < STEPS; ++s)
-        loc[s] = ok[s] ? ldg4(a.le + (cloud_base + (size_t)pn[s]) * LD + ch0 + cl) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const unsigned buf = n % ER_NBUF;
-      er_wait(bar_full(buf), (n / ER_NBUF) & 1u);
-      const float* halo = ring + (size_t)buf * (G::BYTES / 4);
-#pragma unroll
-      for (int s = 0; s < STEPS; ++s) {
-        if (!ok[s]) continue;
-        const uint4 ca = c0[s], cb = c1[s];
-        const size_t row = cloud_base + (size_t)pn[s];
-        const float4 lc = loc[s];
-        const bool esc = ((ca.x | ca.y | ca.z | ca.w | cb.x | cb.y | cb.z | cb.w) & 0x80008000u) != 0u;
-        const float* hbase = halo + pb0[s];
-        f32x2 A_lo = 0ull, A_hi = 0ull, c_lo = 0ull, c_hi = 0ull, o_lo = pack2(0.f, 0.f), o_hi = o_lo;
-        const f32x2 l_lo = pack2(lc.x, lc.y), l_hi = pack2(lc.z, lc.w);
-        if (APPLY) {
-          const float4 A4 = *reinterpret_cast<const float4*>(&coef[ch0 + cl]);
-          const float4 B4 = *reinterpret_cast<const float4*>(&coef[COUT + ch0 + cl]);
-          A_lo = pack2(A4.x, A4.y); A_hi = pack2(A4.z, A4.w);
-          c_lo = pack2(fmaf(-lc.x, A4.x, B4.x), fmaf(-lc.y, A4.y, B4.y));
-          c_hi = pack2(fmaf(-lc.z, A4.z, B4.z), fmaf(-lc.w, A4.w, B4.w));
-        }
-        auto body = [&](const float4 e) {
-          const f32x2 e_lo = pack2(e.x, e.y), e_hi = pack2(e.z, e.w);
-          if (APPLY) {
-            float t0, t1f, t2, t3;
-            unpack2(fma2(e_lo, A_lo, c_lo), t0, t1f);
-            unpack2(fma2(e_hi, A_hi, c_hi), t2, t3);
-            o_lo = add2(o_lo, pack2(fmaxf(t0, 0.f), fmaxf(t1f, 0.f)));
-            o_hi = add2(o_hi, pack2(fmaxf(t2, 0.f), fmaxf(t3, 0.f)));
-          } else {
-            const f32x2 d_lo = sub2(e_lo, l_lo), d_hi = sub2(e_hi, l_hi);
-            acc[slab][0] = add2(acc[slab][0], d_lo); acc[slab][1] = add2(acc[slab][1], d_hi);
-            acc[slab][2] = fma2(d_lo, d_lo, acc[slab][2]); acc[slab][3] = fma2(d_hi, d_hi, acc[slab][3]);
-          }
-        };
-        auto code_of = [&](int k) -> unsigned {
-          const int wq = k >> 1;
-          const unsigned wd = wq == 0 ? ca.x : wq == 1 ? ca.y : wq == 2 ? ca.z : wq == 3 ? ca.w
-                            : wq == 4 ? cb.x : wq == 5 ? cb.y : wq == 6 ? cb.z : cb.w;
-          return (k & 1) ? wd >> 16 : wd & 0xffffu;
-        };
-        if (!esc) {
-#pragma unroll
-          for (int k = 0; k < PMVS_KNN; ++k) body(*reinterpret_cast<const float4*>(hbase + code_of(k) * ET_CP));
-        } else {
-#pragma unroll 1
-          for (int k = 0; k < PMVS_KNN; ++k) {
-            const unsigned c = code_of(k);
-            if (c & 0x8000u) {
-              const int j = (int)(c & 127u);
-              int tt = pn[s] + (j / 25 - 2) * HW + ((j % 25) / 5 - 2) * gw + (j % 5 - 2);
-              tt = tt < 0 ? 0 : (tt > N - 1 ? N - 1 : tt);
-              body(ldg4(a.le + (cloud_base + (size_t)tt) * LD + COUT + ch0 + cl));
-            } else {
-              body(*reinterpret_cast<const float4*>(hbase + c * ET_CP));
-            }
-          }
-        }
-        if (APPLY) {
-          float4 o;
-          unpack2(o_lo, o.x, o.y);
-          unpack2(o_hi, o.z, o.w);
-          float* orow = a.out + row * a.ldo;
-          if (a.concat_central) {
-            const float4 m = *reinterpret_cast<const float4*>(&coef[2 * COUT + ch0 + cl]);
-            const float4 is = *reinterpret_cast<const float4*>(&coef[3 * COUT + ch0 + cl]);
-            const float4 gm = *reinterpret_cast<const float4*>(&coef[4 * COUT + ch0 + cl]);
-            const float4 bt = *reinterpret_cast<const float4*>(&coef[5 * COUT + ch0 + cl]);
-            float4 c;
-            c.x = fmaxf(bn_apply(lc.x, m.x, is.x, gm.x, bt.x), 0.f);
-            c.y = fmaxf(bn_apply(lc.y, m.y, is.y, gm.y, bt.y), 0.f);
-            c.z = fmaxf(bn_apply(lc.z, m.z, is.z, gm.z, bt.z), 0.f);
-            c.w = fmaxf(bn_apply(lc.w, m.w, is.w, gm.w, bt.w), 0.f);
-            st4(orow + ch0 + cl, c);
-            orow += COUT;
-          }
-          constexpr float rk = 1.f / (float)PMVS_KNN;
-          st4(orow + ch0 + cl, make_float4(__fmul_rn(o.x, rk), __fmul_rn(o.y, rk), __fmul_rn(o.z, rk), __fmul_rn(o.w, rk)));
-        }
-      }
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty(buf)) : "memory");
-    }
-  }
-  flush_group();
-}
-
-template <int COUT, bool APPLY>
-int launch_ring(const EdgeTileArgs& a, const CUtensorMap& tm, cudaStream_t st) {
-  using G = TileGeom<8, 4>;
-  constexpr int SMEM = ER_NBUF * G::BYTES;
-  static unsigned long long smem_done = 0;
-  PMVS_TRY(ensure_dyn_smem(edge_ring_kernel<COUT, APPLY>, SMEM, smem_done, "edge_ring"));
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
-  const long long total_tiles = (long long)a.groups * cdiv(a.gw, 8) * cdiv(a.gh, 4) * a.clouds_per_group;
-  const int grid = (int)std::min<long long>(total_tiles, sms);
-  static const char* const names[2][2] = {{"edge_stats_32", "edge_stats_64"}, {"edge_apply_32", "edge_apply_64"}};
-  prof_begin(names[APPLY ? 1 : 0][COUT == 32 ? 0 : 1], st);
-  edge_ring_kernel<COUT, APPLY><<<grid, ER_THREADS, SMEM, st>>>(tm, a);
-  return check_launch(APPLY ? "edge_ring_apply_kernel" : "edge_ring_stats_kernel", st);
-}
-
 template <int COUT, bool APPLY, int TX, int TY>
-int launch_variant(const EdgeTileArgs& a, bool ring_kernel, cudaStream_t st) {
+int launch_variant(const EdgeTileArgs& a, cudaStream_t st) {
   using G = TileGeom<TX, TY>;
   EncodeTiledFn enc = encode_fn();
   if (enc == nullptr) {
@@ -643,7 +333,6 @@ int launch_variant(const EdgeTileArgs& a, bool ring_kernel, cudaStream_t st) {
     set_error("edge_tile: cuTensorMapEncodeTiled failed (%d) for %dx%d, cout %d", (int)r, a.gh, a.gw, COUT);
     return PMVS_ERR_CUDA;
   }
-  if (ring_kernel) return launch_ring<COUT, APPLY>(a, tm, st);
   static unsigned long long smem_done = 0;
   PMVS_TRY(ensure_dyn_smem(edge_tile_kernel<COUT, APPLY, TX, TY>, G::SMEM, smem_done, "edge_tile"));
   // Statistics: persistent CTAs.  Every group (= one BatchNorm population) gets an equal share of the resident CTA
@@ -675,9 +364,11 @@ int launch_edge_tile(const EdgeTileArgs& a, int tile_w, cudaStream_t st) {
                "edge_tile: NULL pointer");
   PMVS_REQUIRE(a.cout == 32 || a.cout == 64, "edge_tile: out_channels %d (supported: 32, 64)", a.cout);
   PMVS_REQUIRE(a.gh > 0 && a.gw > 0 && a.groups > 0 && a.clouds_per_group > 0, "edge_tile: bad cloud shape");
-  // tile_w 16 selects the ring kernel (a 16 x 4 x 5 TILE, 2 CTAs / SM, measured 25 % slower and was dropped)
-  const bool ring_kernel = tile_w == 16;
-  return a.cout == 32 ? launch_variant<32, APPLY, 8, 4>(a, ring_kernel, st) : launch_variant<64, APPLY, 8, 4>(a, ring_kernel, st);
+  // Measured and dropped (git history): a 16 x 4 x 5 tile with 2 CTAs / SM (25 % slower), and a ring variant - one
+  // persistent 21-warp CTA per SM, 3-deep ring of TMA boxes loaded two items ahead - which removed the TMA waits
+  // (23 % of the warp samples here) but ran 4-16 % slower at every iteration size: 20 consumer warps instead of 24.
+  (void)tile_w;
+  return a.cout == 32 ? launch_variant<32, APPLY, 8, 4>(a, st) : launch_variant<64, APPLY, 8, 4>(a, st);
 }
 
 }  // namespace
