@@ -779,4 +779,6 @@ def test_gather_knn_backward_deterministic_segmented_reduce(case):
     assert torch.equal(a, b)
     ref = _scatter_reference(gout.cpu().numpy(), idx.cpu().numpy(), N)
     assert np.array_equal(a.cpu().numpy(), ref)
-    assert torch.allclose(a, atomic, rtol=1e-5, atol=1e-3 if case == "hot_row" else 1e-4)
+    # the atomic scatter adds in arrival order: rows that collect > 1 000 contributions (the clamped aliases of the
+    # out-of-grid picks, the hot row) differ from any fixed order by ~sqrt(n) * |sum| * 2^-24
+    assert torch.allclose(a, atomic, rtol=1e-5, atol=2e-3)
