@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
   auto bar_empty = [&](int s) { return bar0 + 8u * (uint32_t)(STAGES + s); };
   auto bar_accf = [&](int b) { return bar0 + 8u * (uint32_t)(2 * STAGES + b); };
   auto bar_acce = [&](int b) { return bar0 + 8u * (uint32_t)(2 * STAGES + 2 + b); };
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  const uint32_t bar_w = bar0 + 8u * (uint32_t)(2 * STAGES + 4);  // weights are in tensor memory
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 5);
 
   const int K = a.cin;
   const int nch = (K + KC - 1) / KC;
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
         mbar_init(bar_accf(b), 1);
         mbar_init(bar_acce(b), EPI_WARPS);
       }
+      mbar_init(bar_w, EPI_WARPS);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -223,43 +225,54 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
     // ---- weights -> tensor memory (A operand): lane L of TMEM = row L of [W_hi ; W_lo] ----------------
     const int L = warp * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // One row of K floats per thread, in batches of 32 columns: the 8 loads of a batch are in flight together (a
+    // serial 8-column loop cost K/8 dependent L2 round trips = ~10 us of prologue for K = 224).
+    const float* wrow;
+    bool is_hi = true, live = true;
     if (STACKED) {
       // lane quarter q = 16 channels: lanes [0,16) of the quarter hold W_hi[16q + i], lanes [16,32) W_lo[16q + i],
       // so the hi and lo products of a channel meet inside ONE epilogue warp (lane ^ 16), no shared-memory exchange
       const int ch = warp * 16 + (lane & 15);
-      const bool is_hi = lane < 16, live = ch < COUT;
-      const float* wrow = a.w + (size_t)(live ? ch : 0) * K;
-      for (int k0 = 0; k0 < K; k0 += 8) {
-        float v[8];
-        const float4 w0 = ldg4(wrow + k0), w1 = ldg4(wrow + k0 + 4);
-        const float x[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float h = tf32_hi(x[i]);
-          v[i] = !live ? 0.f : (is_hi ? h : __fsub_rn(x[i], h));
-        }
-        tmem_st8(lane_addr + TM_A + k0, v);
-      }
+      is_hi = lane < 16;
+      live = ch < COUT;
+      wrow = a.w + (size_t)(live ? ch : 0) * K;
     } else {
-      const float* wrow = a.w + (size_t)L * K;
-      for (int k0 = 0; k0 < K; k0 += 8) {
-        float vh[8], vl[8];
-        const float4 w0 = ldg4(wrow + k0), w1 = ldg4(wrow + k0 + 4);
-        const float x[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      wrow = a.w + (size_t)L * K;
+    }
+    for (int kb = 0; kb < K; kb += 32) {
+      float4 wv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          vh[i] = tf32_hi(x[i]);
-          vl[i] = __fsub_rn(x[i], vh[i]);
+      for (int i = 0; i < 8; ++i)
+        wv[i] = kb + 4 * i < K ? ldg4(wrow + kb + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kb + 8 * j < K) {  // K is a multiple of 8
+          const float x[8] = {wv[2 * j].x, wv[2 * j].y, wv[2 * j].z, wv[2 * j].w,
+                              wv[2 * j + 1].x, wv[2 * j + 1].y, wv[2 * j + 1].z, wv[2 * j + 1].w};
+          float vh[8], vl[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            vh[i] = tf32_hi(x[i]);
+            vl[i] = __fsub_rn(x[i], vh[i]);
+          }
+          if (STACKED) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = !live ? 0.f : (is_hi ? vh[i] : vl[i]);
+            tmem_st8(lane_addr + TM_A + kb + 8 * j, v);
+          } else {
+            tmem_st8(lane_addr + TM_A + kb + 8 * j, vh);
+            tmem_st8(lane_addr + TM_A2 + kb + 8 * j, vl);
+          }
         }
-        tmem_st8(lane_addr + TM_A + k0, vh);
-        tmem_st8(lane_addr + TM_A2 + k0, vl);
       }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    // only the MMA warp needs the weights: it waits on bar_w; the producers start loading X right away
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_w);
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
 
   if (warp >= PROD_WARP0) {
     // =============================== producers ==========================================================
@@ -434,6 +447,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
       constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       const uint32_t desc_lo0 = (((smem_base + SM_RING) >> 4) & 0x3FFFu) | (1u << 16);
       constexpr uint32_t D_STAGE = STAGE_BYTES >> 4, D_PLANE = PLANE_BYTES >> 4, D_KSTEP = 32 >> 4;
+      mbar_wait(bar_w, 0u);  // [W_hi ; W_lo] written by the four epilogue warps
+      tc_fence_after();
       int n = 0;
       for (int it = 0; it < tr.count; ++it) {
         const int b = it & 1, use = it >> 1;
