@@ -15,10 +15,11 @@
 //     instead of 112) and issues 2 MMAs (M=128, N=128, K=8):  [W_hi;W_lo] * X_hi  and  [W_hi;W_lo] * X_lo.
 //     Accumulator lanes [0,64) hold W_hi*X, lanes [64,128) hold W_lo*X; the epilogue adds them.
 //     cout = 128 uses two A operands (W_hi, W_lo) and two accumulators (3 MMAs per k-step).
-//   * warp-specialised, persistent: 16 producer warps (coalesced 128-bit global loads four chunks ahead
+//   * warp-specialised, persistent: 16 (K > 64) or 8 producer warps (coalesced 128-bit global loads four chunks ahead
 //     in registers -> fused input BatchNorm+ReLU -> TF32 hi/lo split -> K-major SWIZZLE_128B stores
 //     into a 4-stage mbarrier ring), 1 MMA warp (one elected thread: tcgen05.mma, tcgen05.commit frees
-//     the stage), 4 epilogue warps (tcgen05.ld of one accumulator while the MMAs fill the other).
+//     the stage), 4 epilogue warps per accumulator buffer (tcgen05.ld of one accumulator while the MMAs fill the
+//     other; K <= 64 runs one epilogue group per buffer, see Roles).
 //   * the accumulator is TRANSPOSED (lane = output channel, column = point): a warp stores 32
 //     consecutive channels of one point = one full 128-byte line per instruction with no shared-memory
 //     staging, and the BatchNorm statistics of the outputs (per-channel sum / sum of squares) are
@@ -37,13 +38,25 @@ constexpr int NT = 128;                       // points per tile == UMMA N
 constexpr int KC = 32;                        // fp32 K columns per chunk == one 128-byte swizzle row
 constexpr int PLANE_BYTES = NT * KC * 4;      // 16 KB
 constexpr int STAGE_BYTES = 2 * PLANE_BYTES;  // X_hi, X_lo
-constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
-constexpr int MMA_WARP = EPI_WARPS;           // warp 4
-constexpr int PROD_WARP0 = EPI_WARPS + 1;     // warps 5..12
-constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int THREADS = 32 * (EPI_WARPS + 1 + PROD_WARPS);  // 672
+// Warp roles.  EG = 1: 4 epilogue warps, 16 producer warps (672 threads) - the shapes with K > 64, whose main loop is
+// longer than the epilogue.  EG = 2: TWO epilogue groups (one per accumulator buffer: group e drains the tiles with
+// it % 2 == e, so consecutive tiles' epilogues overlap) and 8 producer warps (544 threads) - K = 32 / 64, where a
+// tile's epilogue is longer than its one or two chunks of main loop.  Measured at it.3 (us, EG = 1 / EG = 2):
+// 32->64 39.2 / 33.4, 64->64 59.7 / 53.6, 64->16 57.7 / 49.5, 64->128 65.9 / 63.9, but 136->64 68.0 / 72.1 and
+// 224->64 92.5 / 96.6.
+constexpr int EPI_GROUP = 4;                  // warps of one epilogue group = the 4 TMEM lane quarters
+template <int EG>
+struct Roles {
+  static constexpr int EPI_WARPS = EG * EPI_GROUP;
+  static constexpr int PROD_WARPS = EG == 2 ? 8 : 16;
+  static constexpr int MMA_WARP = EPI_WARPS;
+  static constexpr int PROD_WARP0 = EPI_WARPS + 1;
+  static constexpr int PROD_THREADS = PROD_WARPS * 32;
+  static constexpr int THREADS = 32 * (EPI_WARPS + 1 + PROD_WARPS);  // 672 / 544
+  static constexpr int A_LD = NT * 8 / PROD_THREADS;  // 16-byte pieces per producer thread and chunk (2 / 4)
+  static_assert(A_LD * PROD_THREADS == NT * 8, "the producers share a chunk evenly");
+};
 constexpr int MAXK = 224;
-constexpr int A_LD = NT * 8 / PROD_THREADS;   // float4 loads per producer thread and chunk (2)
 
 // Shared-memory layout.  ASYNC = 0: the producers prefetch through registers (4 chunks ahead) into a 4-stage operand
 // ring.  ASYNC = N > 0: the raw fp32 chunks travel global -> shared memory with cp.async (LDGSTS, no registers
@@ -171,8 +184,11 @@ __device__ __forceinline__ TileRange my_tiles(int total) {
   return TileRange{lo, hi - lo};
 }
 
-template <int COUT, bool IN_BN, int ASYNC, int NSTAGES>
-__global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
+template <int COUT, bool IN_BN, int ASYNC, int NSTAGES, int EG>
+__global__ void __launch_bounds__(Roles<EG>::THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
+  using R = Roles<EG>;
+  constexpr int PROD_WARPS = R::PROD_WARPS, MMA_WARP = R::MMA_WARP, PROD_WARP0 = R::PROD_WARP0;
+  constexpr int PROD_THREADS = R::PROD_THREADS, A_LD = R::A_LD;
   using LY = Layout<ASYNC, NSTAGES>;
   constexpr int STAGES = LY::NST;
   constexpr int SM_RING = LY::RING, SM_STAGING = LY::STAGING, SM_BN = LY::BN, SM_BAR = LY::BAR;
@@ -206,9 +222,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(bar_accf(b), 1);
-        mbar_init(bar_acce(b), EPI_WARPS);
+        mbar_init(bar_acce(b), EPI_GROUP);
       }
-      mbar_init(bar_w, EPI_WARPS);
+      mbar_init(bar_w, EPI_GROUP);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -221,7 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < EPI_WARPS) {
+  if (warp < EPI_GROUP) {
     // ---- weights -> tensor memory (A operand): lane L of TMEM = row L of [W_hi ; W_lo] ----------------
     const int L = warp * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -489,7 +505,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
     }
   } else {
     // =============================== epilogue ===========================================================
-    const int q = warp;  // TMEM lane quarter
+    const int q = warp & (EPI_GROUP - 1);  // TMEM lane quarter
+    const int eg = warp / EPI_GROUP;       // epilogue group = accumulator buffer
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     // stacked: lane 32q + i of the accumulator = W_hi * X (i < 16) or W_lo * X (i >= 16) of channel 16q + (i & 15),
     // column = point.  hi + lo is one shuffle with lane ^ 16; the lower half-warp then owns the even points of the
@@ -515,7 +532,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
 #pragma unroll
       for (int h = 0; h < NCH_T; ++h) acc1[h] = acc2[h] = 0.0;
     };
-    for (int it = 0; it < tr.count; ++it) {
+    for (int it = eg; it < tr.count; it += EG) {
       const int t = tr.first + it;
       const int g = t / tpg, row0 = (t - g * tpg) * NT;
       const int rows_valid = min(NT, a.rows_per_group - row0);
@@ -604,11 +621,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs a) {
   }
 }
 
-template <int COUT, bool IN_BN, int ASYNC, int NSTAGES>
+template <int COUT, bool IN_BN, int ASYNC, int NSTAGES, int EG>
 static int launch_pf(const GemmArgs& a, cudaStream_t st, const char* name) {
   constexpr int SM_TOTAL = Layout<ASYNC, NSTAGES>::TOTAL;
   static unsigned long long smem_done = 0;
-  PMVS_TRY((ensure_dyn_smem(gemm_ws_kernel<COUT, IN_BN, ASYNC, NSTAGES>, SM_TOTAL, smem_done, "gemm_ws")));
+  PMVS_TRY((ensure_dyn_smem(gemm_ws_kernel<COUT, IN_BN, ASYNC, NSTAGES, EG>, SM_TOTAL, smem_done, "gemm_ws")));
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -618,7 +635,7 @@ static int launch_pf(const GemmArgs& a, cudaStream_t st, const char* name) {
   const long long tiles = (long long)a.groups * cdiv(a.rows_per_group, NT);
   const int grid = (int)std::min<long long>(tiles, num_sms);
   prof_begin(name, st);
-  gemm_ws_kernel<COUT, IN_BN, ASYNC, NSTAGES><<<grid, THREADS, SM_TOTAL, st>>>(a);
+  gemm_ws_kernel<COUT, IN_BN, ASYNC, NSTAGES, EG><<<grid, Roles<EG>::THREADS, SM_TOTAL, st>>>(a);
   return check_launch("gemm_ws_kernel", st);
 }
 template <int COUT, bool IN_BN>
@@ -626,8 +643,10 @@ static int launch_one(const GemmArgs& a, cudaStream_t st, const char* name) {
   // Depth variants measured within 1 % of each other at BASELINE C2 (staging 3..7 stages x operand 2..4 stages, round 2):
   // the kernels sit at ~70 % of what a read-dominated stream reaches on this part (profiles/r02/hbm_read_probe.txt),
   // not at a pipeline-depth limit.  Two are kept: the default and the register-prefetch form.
-  if (opt(OPT_GEMM) == 1) return launch_pf<COUT, IN_BN, 0, 4>(a, st, name);  // register prefetch, 4 chunks in flight, 4 operand stages
-  return launch_pf<COUT, IN_BN, 5, 3>(a, st, name);  // cp.async staging: 4 chunks (64 KB) in flight, 3 operand stages
+  if (opt(OPT_GEMM) == 1) return launch_pf<COUT, IN_BN, 0, 4, 1>(a, st, name);  // register prefetch, 4 chunks in flight, 4 operand stages
+  // cp.async staging: 4 chunks (64 KB) in flight, 3 operand stages; two epilogue groups when the main loop is short
+  if (a.cin <= 64) return launch_pf<COUT, IN_BN, 5, 3, 2>(a, st, name);
+  return launch_pf<COUT, IN_BN, 5, 3, 1>(a, st, name);
 }
 
 }  // namespace ws
