@@ -1,12 +1,12 @@
 #!/usr/bin/env bash
-# Build libpmvs_b200.so with experimental compile flags, run the GPU parity suite and a short bench,
-# then restore the default build.  For the GPU box:
-#   gpurun -- 'bash tests/try_experimental.sh -DPMVS_EDGE_TILE=1'
-#   gpurun -- 'bash tests/try_experimental.sh -DPMVS_F32X2=1'
+# Build libpmvs_b200.so with extra nvcc flags (e.g. a -D switch while a kernel variant is being developed), run the GPU
+# parity suite and a short bench, then restore the default build.  For the GPU box:
+#   gpurun -- 'bash tests/try_experimental.sh -DSOME_SWITCH=1'
 # or, to keep nvcc time off the GPU box, build a side copy in the build container first and pass it:
-#   PMVS_OUT=$PWD/altlibs/tile.so bash pointmvsnet_b200/csrc/build.sh -DPMVS_EDGE_TILE=1
-#   gpurun -- 'bash tests/try_experimental.sh altlibs/tile.so'
-# Flags are described in pointmvsnet_b200/csrc/common.cuh and DESIGN.md section 8.
+#   PMVS_OUT=$PWD/altlibs/variant.so bash pointmvsnet_b200/csrc/build.sh -DSOME_SWITCH=1
+#   gpurun -- 'bash tests/try_experimental.sh altlibs/variant.so'
+# Variants that exist at run time are compared without rebuilding: PMVS_OPTIONS="edge=0,gemm=1" (include/pmvs_b200.h)
+# and  python tests/profile_per_launch.py C2 "edge=1" "edge=0"  (per-launch CUDA-event times of one pass).
 set -uo pipefail
 cd "$(dirname "${BASH_SOURCE[0]}")/.."
 mkdir -p gpurun_out
