@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(Roles<EG>::THREADS, 1) gemm_ws_kernel(const Ge
   constexpr bool STACKED = COUT <= 64;
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B operands need 1024-byte alignment
   const uint32_t smem_base = smem_u32(smem);
-  float* sBN = (float*)(smem + SM_BN);  // mean, istd, gamma, beta x MAXK
+  float* sBN = (float*)(smem + SM_BN);  // input BatchNorm as one FMA per element: A = istd * gamma | B = beta - mean * A, x MAXK
   uint64_t* bars = (uint64_t*)(smem + SM_BAR);
   // bars: full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]; then the TMEM base slot
   const uint32_t bar0 = smem_u32(bars);
@@ -372,10 +372,10 @@ __global__ void __launch_bounds__(Roles<EG>::THREADS, 1) gemm_ws_kernel(const Ge
           const double* s = a.in_stats + (size_t)g * 2 * K;
           for (int cc = ptid; cc < K; cc += PROD_THREADS) {
             const BnCoef k = bn_coef(s[cc], s[K + cc], a.in_count, a.eps);
-            sBN[cc] = k.mean;
-            sBN[MAXK + cc] = k.invstd;
-            sBN[2 * MAXK + cc] = a.in_gamma[cc];
-            sBN[3 * MAXK + cc] = a.in_beta[cc];
+            // the same coefficient form as the EdgeConv apply kernels (edge_tile.cu): relu(fma(x, A, B))
+            const float A = __fmul_rn(k.invstd, a.in_gamma[cc]);
+            sBN[cc] = A;
+            sBN[MAXK + cc] = fmaf(-k.mean, A, a.in_beta[cc]);
           }
           named_bar_sync(1, PROD_THREADS);
           cur_g = g;
@@ -397,15 +397,13 @@ __global__ void __launch_bounds__(Roles<EG>::THREADS, 1) gemm_ws_kernel(const Ge
           // rows / columns beyond the valid range were loaded as zeros and must stay zero
           const int r = prow + ROWS_STEP * i;
           if (k0 < K && r < a.rows_per_group - cp.row0) {
-            // k0 is a multiple of 4 and the four tables start MAXK floats apart: four 128-bit loads
-            const float4 m = *reinterpret_cast<const float4*>(&sBN[k0]);
-            const float4 is = *reinterpret_cast<const float4*>(&sBN[MAXK + k0]);
-            const float4 gm = *reinterpret_cast<const float4*>(&sBN[2 * MAXK + k0]);
-            const float4 bt = *reinterpret_cast<const float4*>(&sBN[3 * MAXK + k0]);
-            v.x = fmaxf(bn_apply(v.x, m.x, is.x, gm.x, bt.x), 0.f);
-            v.y = fmaxf(bn_apply(v.y, m.y, is.y, gm.y, bt.y), 0.f);
-            v.z = fmaxf(bn_apply(v.z, m.z, is.z, gm.z, bt.z), 0.f);
-            v.w = fmaxf(bn_apply(v.w, m.w, is.w, gm.w, bt.w), 0.f);
+            // k0 is a multiple of 4 and the two tables start MAXK floats apart: two 128-bit loads
+            const float4 A4 = *reinterpret_cast<const float4*>(&sBN[k0]);
+            const float4 B4 = *reinterpret_cast<const float4*>(&sBN[MAXK + k0]);
+            v.x = fmaxf(fmaf(v.x, A4.x, B4.x), 0.f);
+            v.y = fmaxf(fmaf(v.y, A4.y, B4.y), 0.f);
+            v.z = fmaxf(fmaf(v.z, A4.z, B4.z), 0.f);
+            v.w = fmaxf(fmaf(v.w, A4.w, B4.w), 0.f);
           }
         }
         float4 hi, lo;
