@@ -212,7 +212,6 @@ __global__ void __launch_bounds__(Roles<EG>::THREADS, 1) gemm_ws_kernel(const Ge
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tpg = (a.rows_per_group + NT - 1) / NT;  // tiles per group
   const TileRange tr = my_tiles(a.groups * tpg);
-  constexpr bool in_bn = IN_BN;
 
   if (warp == MMA_WARP) {
     if (lane == 0) {
@@ -332,7 +331,7 @@ __global__ void __launch_bounds__(Roles<EG>::THREADS, 1) gemm_ws_kernel(const Ge
         const bool ok = kvalid && r < rows_valid;
         if (ASYNC > 0) {
           // 16 bytes global -> this thread's own slot of the staging stage; src-size 0 zero-fills (padding rows / columns)
-          const uint32_t dst = smem_base + SM_STAGING + (n_issued % ASYNC) * PLANE_BYTES + (ptid + PROD_THREADS * i) * 16;
+          const uint32_t dst = smem_base + SM_STAGING + (n_issued % (ASYNC > 0 ? ASYNC : 1)) * PLANE_BYTES + (ptid + PROD_THREADS * i) * 16;
           const float* src = ok ? ci.ptr + (size_t)(ROWS_STEP * i) * a.ldx : a.x;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
         } else {

@@ -290,3 +290,15 @@ def test_image_conv_producer_names_layout_and_probability_map():
     depth = torch.tensor([10.5, 12.0, 99.0]).view(1, 1, 1, 3)  # between planes 0/1, exactly plane 2, beyond the last
     pm = get_propability_map(cv, depth, torch.tensor([10.0]), torch.tensor([1.0]))
     assert torch.allclose(pm.view(-1), torch.tensor([.1 + .2, .4 + .4, .1 + .1]))
+
+
+def test_deterministic_gather_backward_workspace_size_is_host_only():
+    """pmvs_gather_knn_backward_det_workspace_bytes is plain host arithmetic (callable without a GPU): two int32 arrays
+    of B*N counters, B*(N+1) offsets and B*N*K list entries, each 256-byte aligned."""
+    from pointmvsnet_b200 import _lib
+    f = _lib.lib.pmvs_gather_knn_backward_det_workspace_bytes
+    assert f(0, 0, 0) >= 0 and f(-1, 4, 4) == 0
+    B, N, K = 2, 1200, 16
+    need = 4 * (2 * B * N + B * (N + 1) + B * N * K)
+    assert need <= f(B, N, K) <= need + 5 * 256
+    assert f(1, 102400, 16) > f(1, 25600, 16) > 0
