@@ -394,7 +394,7 @@ extern "C" int pmvs_point_flow_iter(const pmvs_flow_shape* shape, const pmvs_flo
   f.ratio = shape->ratio; f.sub_begin = p.sub_begin; f.sub_count = S;
   PMVS_TRY(launch_fused_fetch(f, st));
 
-  // a10: neighbour lists.  The tile EdgeConv path consumes 1-byte candidate ids; the int32 row indices are only
+  // a10: neighbour lists.  The tile EdgeConv path consumes 16-bit neighbour codes; the int32 row indices are only
   // materialised for the gather path (or on request, for the tests)
   const int edge_impl = opt(OPT_EDGE);
   unsigned short* cand = (unsigned short*)(ws + p.cand);
