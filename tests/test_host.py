@@ -174,6 +174,33 @@ full_pyr = [torch.randn(1, V, c, 4, 6, generator=g) for c in (16, 32, 64)]
 own = shard_views(V, rank, world)
 got = gather_view_pyramids([lv[:, own] for lv in full_pyr], V, rank, world)
 assert all(torch.equal(a, b) for a, b in zip(got, full_pyr))
+# C5 latency split: SubCloudShardedPass drives a point-flow callable per iteration with this rank's range of
+# sub-clouds and re-assembles the map with one all-reduce.  A CPU stand-in for the fused module (writes a value that
+# encodes iteration, sub-cloud and the previous depth into exactly the pixels of the requested sub-clouds) checks the
+# control flow: every rank ends with the map a single process computes.
+from pointmvsnet_b200.parallel import SubCloudShardedPass
+import torch.nn.functional as F
+class FakeFlow(object):
+    update_running_stats = True
+    def __call__(self, depth, interval, scale, it, out=None, sub_range=None, img_hw=None, **kw):
+        r = int(scale * 8)
+        h, w = int(img_hw[0] * scale), int(img_hw[1] * scale)
+        prev = F.interpolate(depth, (h, w), mode="nearest")
+        first, count = sub_range if sub_range is not None else (0, r * r)
+        ys = torch.arange(h).view(h, 1).expand(h, w)
+        xs = torch.arange(w).view(1, w).expand(h, w)
+        sid = (ys %% r) * r + (xs %% r)
+        mine = (sid >= first) & (sid < first + count)
+        val = prev[:, 0] * 2.0 + 1000.0 * (it + 1) + sid.float()
+        out[0][:, 0][:, mine] = val[:, mine]
+        return out
+img_hw = (32, 48)
+coarse = torch.arange(4 * 6, dtype=torch.float32).view(1, 1, 4, 6)
+single = SubCloudShardedPass(FakeFlow(), 0, 1).run(None, coarse, None, None, None, None, img_hw)
+ff = FakeFlow()
+sharded = SubCloudShardedPass(ff, rank, world).run(None, coarse, None, None, None, None, img_hw)
+assert ff.update_running_stats is False
+assert sharded.shape == (1, 1, 16, 24) and torch.equal(sharded, single), (sharded - single).abs().max()
 dist.barrier()
 dist.destroy_process_group()
 print("OK", rank)
